@@ -1,0 +1,369 @@
+// PyTorch bindings for the sm_100a kernels.  Thin by design: shape logic lives in Python
+// (baton_b200/ops), this file only unwraps tensors, picks the current stream and checks codes.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <optional>
+#include <vector>
+
+#include "launch.h"
+
+namespace {
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+inline void check(int rc, const char* what) {
+  TORCH_CHECK(rc == 0, "baton_b200::", what, " failed with code ", rc,
+              rc > 0 ? std::string(" (") + cudaGetErrorString(static_cast<cudaError_t>(rc)) + ")" : std::string());
+}
+inline const void* cptr(const at::Tensor& t) { return t.data_ptr(); }
+inline void* ptr(at::Tensor& t) { return t.data_ptr(); }
+template <class T>
+inline T* opt_ptr(const std::optional<at::Tensor>& t) {
+  return (t.has_value() && t->defined()) ? reinterpret_cast<T*>(t->data_ptr()) : nullptr;
+}
+#define CHECK_CUDA(x) TORCH_CHECK((x).is_cuda(), #x " must be a CUDA tensor")
+
+void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::optional<at::Tensor>& bias, int64_t M,
+          int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd, bool a_mn, bool b_mn, int64_t act,
+          int64_t split_k, bool accumulate, double alpha, const std::optional<at::Tensor>& flags, int64_t flag_epoch,
+          int64_t flag_elem_off, int64_t flag_tile_elems, int64_t force_bn, bool simt) {
+  CHECK_CUDA(a); CHECK_CUDA(b); CHECK_CUDA(d);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm operands must be bf16");
+  TORCH_CHECK(d.scalar_type() == at::kBFloat16 || d.scalar_type() == at::kFloat, "gemm output must be bf16/fp32");
+  const c10::cuda::CUDAGuard guard(a.device());
+  const int out_fp32 = d.scalar_type() == at::kFloat;
+  const float* bp = opt_ptr<const float>(bias);
+  if (simt) {
+    check(b200_gemm_simt(cptr(a), cptr(b), ptr(d), bp, M, N, K, lda, ldb, ldd, a_mn, b_mn, out_fp32, act, accumulate,
+                         static_cast<float>(alpha), cur_stream()),
+          "gemm_simt");
+    return;
+  }
+  check(b200_gemm_bf16(cptr(a), cptr(b), ptr(d), bp, M, N, K, lda, ldb, ldd, a_mn, b_mn, out_fp32, act, split_k,
+                       accumulate, static_cast<float>(alpha), opt_ptr<const uint32_t>(flags),
+                       static_cast<uint32_t>(flag_epoch), flag_elem_off, static_cast<int>(flag_tile_elems),
+                       static_cast<int>(force_bn), cur_stream()),
+        "gemm_bf16");
+}
+
+void fused_sgd(at::Tensor w, at::Tensor g, const std::optional<at::Tensor>& mom, const std::optional<at::Tensor>& wb,
+               const at::Tensor& hyper, bool zero_grad, bool nesterov) {
+  CHECK_CUDA(w);
+  TORCH_CHECK(w.scalar_type() == at::kFloat && g.scalar_type() == at::kFloat && hyper.scalar_type() == at::kFloat);
+  TORCH_CHECK(w.is_contiguous() && g.is_contiguous() && w.numel() == g.numel());
+  const c10::cuda::CUDAGuard guard(w.device());
+  check(b200_fused_sgd(w.data_ptr<float>(), g.data_ptr<float>(), opt_ptr<float>(mom), opt_ptr<void>(wb), w.numel(),
+                       hyper.data_ptr<float>(), zero_grad, nesterov, cur_stream()),
+        "fused_sgd");
+}
+
+void weighted_sum(at::Tensor dst, const std::vector<at::Tensor>& srcs, const std::vector<double>& weights) {
+  CHECK_CUDA(dst);
+  TORCH_CHECK(srcs.size() == weights.size() && !srcs.empty() && srcs.size() <= B200_MAX_RANKS);
+  TORCH_CHECK(dst.is_contiguous());
+  const c10::cuda::CUDAGuard guard(dst.device());
+  std::vector<const void*> ps;
+  std::vector<float> ws;
+  for (size_t i = 0; i < srcs.size(); ++i) {
+    TORCH_CHECK(srcs[i].is_cuda() && srcs[i].is_contiguous() && srcs[i].scalar_type() == dst.scalar_type() &&
+                srcs[i].numel() == dst.numel());
+    ps.push_back(srcs[i].data_ptr());
+    ws.push_back(static_cast<float>(weights[i]));
+  }
+  const int dt = dst.scalar_type() == at::kBFloat16 ? 1 : 0;
+  TORCH_CHECK(dt == 1 || dst.scalar_type() == at::kFloat, "weighted_sum supports fp32/bf16");
+  check(b200_weighted_sum(dst.data_ptr(), ps.data(), ws.data(), static_cast<int>(ps.size()), dst.numel(), dt,
+                          cur_stream()),
+        "weighted_sum");
+}
+
+void cast(const at::Tensor& src, at::Tensor dst) {
+  CHECK_CUDA(src);
+  TORCH_CHECK(src.is_contiguous() && dst.is_contiguous() && src.numel() == dst.numel());
+  const c10::cuda::CUDAGuard guard(src.device());
+  if (src.scalar_type() == at::kFloat && dst.scalar_type() == at::kBFloat16)
+    check(b200_cast_f32_bf16(src.data_ptr<float>(), dst.data_ptr(), src.numel(), cur_stream()), "cast");
+  else if (src.scalar_type() == at::kBFloat16 && dst.scalar_type() == at::kFloat)
+    check(b200_cast_bf16_f32(src.data_ptr(), dst.data_ptr<float>(), src.numel(), cur_stream()), "cast");
+  else
+    TORCH_CHECK(false, "cast: unsupported dtype pair");
+}
+
+void gather_rows(const at::Tensor& src, const at::Tensor& idx, at::Tensor dst) {
+  CHECK_CUDA(src);
+  TORCH_CHECK(idx.scalar_type() == at::kLong && src.is_contiguous() && dst.is_contiguous());
+  const c10::cuda::CUDAGuard guard(src.device());
+  const int64_t n = idx.numel();
+  if (src.scalar_type() == at::kLong && src.dim() == 1) {
+    check(b200_gather_rows_i64(src.data_ptr<int64_t>() ? reinterpret_cast<const long long*>(src.data_ptr<int64_t>()) : nullptr,
+                               reinterpret_cast<const long long*>(idx.data_ptr<int64_t>()),
+                               reinterpret_cast<long long*>(dst.data_ptr<int64_t>()), n, cur_stream()),
+          "gather_i64");
+    return;
+  }
+  const int64_t row_bytes = src.numel() / src.size(0) * src.element_size();
+  check(b200_gather_rows(src.data_ptr(), reinterpret_cast<const long long*>(idx.data_ptr<int64_t>()), dst.data_ptr(), n,
+                         row_bytes, cur_stream()),
+        "gather_rows");
+}
+
+void colsum(const at::Tensor& x, at::Tensor out, int64_t rows, int64_t cols, bool accumulate) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_colsum(x.data_ptr(), out.data_ptr<float>(), rows, cols, accumulate, cur_stream()), "colsum");
+}
+void add_bf16(const at::Tensor& a, const at::Tensor& b, at::Tensor o, bool relu) {
+  CHECK_CUDA(a);
+  const c10::cuda::CUDAGuard guard(a.device());
+  check(b200_add_bf16(a.data_ptr(), b.data_ptr(), o.data_ptr(), a.numel(), relu, cur_stream()), "add_bf16");
+}
+void relu_bwd(const at::Tensor& y, const at::Tensor& dy, at::Tensor dx) {
+  CHECK_CUDA(y);
+  const c10::cuda::CUDAGuard guard(y.device());
+  check(b200_relu_bwd_bf16(y.data_ptr(), dy.data_ptr(), dx.data_ptr(), y.numel(), cur_stream()), "relu_bwd");
+}
+void gelu(const at::Tensor& x, at::Tensor y) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_gelu_bf16(x.data_ptr(), y.data_ptr(), x.numel(), cur_stream()), "gelu");
+}
+void gelu_bwd(const at::Tensor& x, const at::Tensor& dy, at::Tensor dx) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_gelu_bwd_bf16(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), cur_stream()), "gelu_bwd");
+}
+void pad_rows(const at::Tensor& s, at::Tensor d, int64_t rows, int64_t k, int64_t kp) {
+  CHECK_CUDA(s);
+  const c10::cuda::CUDAGuard guard(s.device());
+  check(b200_pad_rows_bf16(s.data_ptr(), d.data_ptr(), rows, k, kp, cur_stream()), "pad_rows");
+}
+
+// ---- fused FedAvg collective -------------------------------------------------------------------
+void fedavg_allreduce(const std::vector<int64_t>& wire_ptrs, const std::vector<int64_t>& pad_ptrs, int64_t wire_mc,
+                      at::Tensor theta, const std::optional<at::Tensor>& global_w,
+                      const std::optional<at::Tensor>& theta_bf16, const std::optional<at::Tensor>& momentum,
+                      const std::optional<at::Tensor>& int_local, const std::vector<int64_t>& int_wire_ptrs,
+                      const std::vector<double>& weights, int64_t alive_mask, int64_t rank, int64_t world, bool wire_bf16,
+                      bool delta, bool use_nvls, int64_t epoch, const std::optional<at::Tensor>& tile_flags,
+                      int64_t flag_value, int64_t tile_elems, int64_t n_ctas, int64_t timeout_log2,
+                      const std::optional<at::Tensor>& status) {
+  CHECK_CUDA(theta);
+  TORCH_CHECK(world <= B200_MAX_RANKS && static_cast<int64_t>(wire_ptrs.size()) == world &&
+              static_cast<int64_t>(pad_ptrs.size()) == world && static_cast<int64_t>(weights.size()) == world);
+  TORCH_CHECK(theta.scalar_type() == at::kFloat && theta.is_contiguous());
+  const c10::cuda::CUDAGuard guard(theta.device());
+  FedAvgArgs a = {};
+  for (int64_t k = 0; k < world; ++k) {
+    a.wire[k] = reinterpret_cast<void*>(wire_ptrs[k]);
+    a.pads[k] = reinterpret_cast<uint32_t*>(pad_ptrs[k]);
+    a.weights[k] = static_cast<float>(weights[k]);
+    a.int_wire[k] = k < static_cast<int64_t>(int_wire_ptrs.size()) ? reinterpret_cast<long long*>(int_wire_ptrs[k]) : nullptr;
+  }
+  a.wire_mc = reinterpret_cast<void*>(wire_mc);
+  a.theta = theta.data_ptr<float>();
+  a.global_w = opt_ptr<float>(global_w);
+  a.theta_bf16 = opt_ptr<void>(theta_bf16);
+  a.momentum = opt_ptr<float>(momentum);
+  a.int_local = opt_ptr<long long>(int_local);
+  a.n_int = (int_local.has_value() && int_local->defined()) ? static_cast<int>(int_local->numel()) : 0;
+  a.alive_mask = static_cast<uint32_t>(alive_mask);
+  a.rank = static_cast<int>(rank);
+  a.world = static_cast<int>(world);
+  a.n = theta.numel();
+  a.wire_bf16 = wire_bf16;
+  a.delta = delta;
+  a.use_nvls = use_nvls;
+  a.epoch = static_cast<uint32_t>(epoch);
+  a.tile_flags = opt_ptr<uint32_t>(tile_flags);
+  a.flag_value = static_cast<uint32_t>(flag_value);
+  a.tile_elems = static_cast<int>(tile_elems);
+  a.timeout_cycles_log2 = static_cast<int>(timeout_log2);
+  a.status = opt_ptr<int>(status);
+  TORCH_CHECK(!delta || a.global_w != nullptr, "delta mode needs the global copy");
+  TORCH_CHECK(!use_nvls || a.wire_mc != nullptr, "NVLS mode needs the multicast address");
+  check(b200_fedavg_allreduce(&a, static_cast<int>(n_ctas), cur_stream()), "fedavg_allreduce");
+}
+
+void flag_barrier(const std::vector<int64_t>& pad_ptrs, int64_t rank, int64_t world, int64_t alive_mask, int64_t epoch,
+                  int64_t slot) {
+  std::vector<uint32_t*> pads;
+  for (auto p : pad_ptrs) pads.push_back(reinterpret_cast<uint32_t*>(p));
+  check(b200_flag_barrier(pads.data(), rank, world, static_cast<uint32_t>(alive_mask), static_cast<uint32_t>(epoch), slot,
+                          cur_stream()),
+        "flag_barrier");
+}
+
+// ---- conv plumbing -------------------------------------------------------------------------------
+void im2col(const at::Tensor& x, at::Tensor col, int64_t N, int64_t H, int64_t W, int64_t C, int64_t KH, int64_t KW,
+            int64_t stride, int64_t pad, int64_t Ho, int64_t Wo, int64_t kp) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_im2col_nhwc(x.data_ptr(), col.data_ptr(), N, H, W, C, KH, KW, stride, pad, Ho, Wo, kp, cur_stream()),
+        "im2col");
+}
+void col2im(const at::Tensor& col, at::Tensor dx, int64_t N, int64_t H, int64_t W, int64_t C, int64_t KH, int64_t KW,
+            int64_t stride, int64_t pad, int64_t Ho, int64_t Wo, int64_t kp) {
+  CHECK_CUDA(col);
+  const c10::cuda::CUDAGuard guard(col.device());
+  check(b200_col2im_nhwc(col.data_ptr(), dx.data_ptr(), N, H, W, C, KH, KW, stride, pad, Ho, Wo, kp, cur_stream()),
+        "col2im");
+}
+void maxpool(const at::Tensor& x, at::Tensor y, at::Tensor arg, int64_t N, int64_t H, int64_t W, int64_t C, int64_t k,
+             int64_t stride, int64_t pad, int64_t Ho, int64_t Wo) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_maxpool_nhwc(x.data_ptr(), y.data_ptr(), arg.data_ptr<int>(), N, H, W, C, k, stride, pad, Ho, Wo,
+                          cur_stream()),
+        "maxpool");
+}
+void maxpool_bwd(const at::Tensor& dy, const at::Tensor& arg, at::Tensor dx, int64_t N, int64_t H, int64_t W, int64_t C,
+                 int64_t Ho, int64_t Wo, int64_t k, int64_t stride, int64_t pad) {
+  CHECK_CUDA(dy);
+  const c10::cuda::CUDAGuard guard(dy.device());
+  check(b200_maxpool_bwd_nhwc(dy.data_ptr(), arg.data_ptr<int>(), dx.data_ptr(), N, H, W, C, Ho, Wo, k, stride, pad,
+                              cur_stream()),
+        "maxpool_bwd");
+}
+void avgpool(const at::Tensor& x, at::Tensor y, int64_t N, int64_t HW, int64_t C) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_avgpool_nhwc(x.data_ptr(), y.data_ptr(), N, HW, C, cur_stream()), "avgpool");
+}
+void avgpool_bwd(const at::Tensor& dy, at::Tensor dx, int64_t N, int64_t HW, int64_t C) {
+  CHECK_CUDA(dy);
+  const c10::cuda::CUDAGuard guard(dy.device());
+  check(b200_avgpool_bwd_nhwc(dy.data_ptr(), dx.data_ptr(), N, HW, C, cur_stream()), "avgpool_bwd");
+}
+
+// ---- normalisation ---------------------------------------------------------------------------------
+void bn_stats(const at::Tensor& x, at::Tensor sums, int64_t rows, int64_t C) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_bn_stats(x.data_ptr(), sums.data_ptr<float>(), rows, C, cur_stream()), "bn_stats");
+}
+void bn_apply(const at::Tensor& x, const std::optional<at::Tensor>& res, at::Tensor y, at::Tensor sums,
+              const std::optional<at::Tensor>& gamma, const std::optional<at::Tensor>& beta,
+              const std::optional<at::Tensor>& rmean, const std::optional<at::Tensor>& rvar, at::Tensor save_mean,
+              at::Tensor save_rstd, const std::optional<at::Tensor>& nbt, int64_t rows, int64_t C, double eps,
+              double momentum, bool relu, bool training) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_bn_apply(x.data_ptr(), opt_ptr<const void>(res), y.data_ptr(), sums.data_ptr<float>(),
+                      opt_ptr<const float>(gamma), opt_ptr<const float>(beta), opt_ptr<float>(rmean),
+                      opt_ptr<float>(rvar), save_mean.data_ptr<float>(), save_rstd.data_ptr<float>(),
+                      opt_ptr<long long>(nbt), rows, C,
+                      static_cast<float>(eps), static_cast<float>(momentum), relu, training, cur_stream()),
+        "bn_apply");
+}
+void bn_bwd_reduce(const at::Tensor& x, const at::Tensor& y, const at::Tensor& dy, const at::Tensor& mean,
+                   const at::Tensor& rstd, at::Tensor sums, int64_t rows, int64_t C, bool relu) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_bn_bwd_reduce(x.data_ptr(), y.data_ptr(), dy.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                           sums.data_ptr<float>(), rows, C, relu, cur_stream()),
+        "bn_bwd_reduce");
+}
+void bn_bwd_apply(const at::Tensor& x, const at::Tensor& y, const at::Tensor& dy, at::Tensor dx,
+                  const std::optional<at::Tensor>& dres, const std::optional<at::Tensor>& gamma, const at::Tensor& mean,
+                  const at::Tensor& rstd, at::Tensor sums, const std::optional<at::Tensor>& dgamma,
+                  const std::optional<at::Tensor>& dbeta, int64_t rows, int64_t C, bool relu) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_bn_bwd_apply(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(), opt_ptr<void>(dres),
+                          opt_ptr<const float>(gamma), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                          sums.data_ptr<float>(), opt_ptr<float>(dgamma), opt_ptr<float>(dbeta), rows, C, relu,
+                          cur_stream()),
+        "bn_bwd_apply");
+}
+void layernorm_fwd(const at::Tensor& x, const std::optional<at::Tensor>& res, at::Tensor y, const at::Tensor& gamma,
+                   const at::Tensor& beta, at::Tensor mean, at::Tensor rstd, int64_t rows, int64_t C, double eps) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_layernorm_fwd(x.data_ptr(), opt_ptr<const void>(res), y.data_ptr(), gamma.data_ptr<float>(),
+                           beta.data_ptr<float>(), mean.data_ptr<float>(), rstd.data_ptr<float>(), rows, C,
+                           static_cast<float>(eps), cur_stream()),
+        "layernorm_fwd");
+}
+void layernorm_bwd(const at::Tensor& x, const at::Tensor& dy, at::Tensor dx, const at::Tensor& gamma,
+                   const at::Tensor& mean, const at::Tensor& rstd, at::Tensor dgamma, at::Tensor dbeta, int64_t rows,
+                   int64_t C) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_layernorm_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), gamma.data_ptr<float>(), mean.data_ptr<float>(),
+                           rstd.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), rows, C,
+                           cur_stream()),
+        "layernorm_bwd");
+}
+void softmax_fwd(const at::Tensor& x, at::Tensor y, int64_t rows, int64_t C, double scale) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_softmax_fwd(x.data_ptr(), y.data_ptr(), rows, C, static_cast<float>(scale), cur_stream()), "softmax_fwd");
+}
+void softmax_bwd(const at::Tensor& y, const at::Tensor& dy, at::Tensor dx, int64_t rows, int64_t C, double scale) {
+  CHECK_CUDA(y);
+  const c10::cuda::CUDAGuard guard(y.device());
+  check(b200_softmax_bwd(y.data_ptr(), dy.data_ptr(), dx.data_ptr(), rows, C, static_cast<float>(scale), cur_stream()),
+        "softmax_bwd");
+}
+
+// ---- losses ------------------------------------------------------------------------------------------
+void softmax_xent(const at::Tensor& logits, const at::Tensor& target, const std::optional<at::Tensor>& dlogits,
+                  at::Tensor loss_acc, int64_t rows, int64_t C, int64_t ld, double grad_scale) {
+  CHECK_CUDA(logits);
+  TORCH_CHECK(target.scalar_type() == at::kLong && loss_acc.scalar_type() == at::kFloat && loss_acc.numel() >= 2);
+  const c10::cuda::CUDAGuard guard(logits.device());
+  const int in32 = logits.scalar_type() == at::kFloat;
+  const int out32 = dlogits.has_value() && dlogits->defined() && dlogits->scalar_type() == at::kFloat;
+  check(b200_softmax_xent(logits.data_ptr(), in32, reinterpret_cast<const long long*>(target.data_ptr<int64_t>()),
+                          opt_ptr<void>(dlogits), out32, loss_acc.data_ptr<float>(), rows, C, ld,
+                          static_cast<float>(grad_scale), cur_stream()),
+        "softmax_xent");
+}
+void mse(const at::Tensor& pred, const at::Tensor& target, const std::optional<at::Tensor>& dpred, at::Tensor loss_acc,
+         double grad_scale) {
+  CHECK_CUDA(pred);
+  TORCH_CHECK(target.scalar_type() == at::kFloat && target.numel() == pred.numel());
+  const c10::cuda::CUDAGuard guard(pred.device());
+  const int in32 = pred.scalar_type() == at::kFloat;
+  const int out32 = dpred.has_value() && dpred->defined() && dpred->scalar_type() == at::kFloat;
+  check(b200_mse(pred.data_ptr(), in32, target.data_ptr<float>(), opt_ptr<void>(dpred), out32,
+                 loss_acc.data_ptr<float>(), pred.numel(), static_cast<float>(grad_scale), cur_stream()),
+        "mse");
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "baton_b200 sm_100a kernels";
+  m.attr("MAX_RANKS") = B200_MAX_RANKS;
+  m.def("gemm", &gemm);
+  m.def("fused_sgd", &fused_sgd);
+  m.def("weighted_sum", &weighted_sum);
+  m.def("cast", &cast);
+  m.def("gather_rows", &gather_rows);
+  m.def("colsum", &colsum);
+  m.def("add_bf16", &add_bf16);
+  m.def("relu_bwd", &relu_bwd);
+  m.def("gelu", &gelu);
+  m.def("gelu_bwd", &gelu_bwd);
+  m.def("pad_rows", &pad_rows);
+  m.def("fedavg_allreduce", &fedavg_allreduce);
+  m.def("flag_barrier", &flag_barrier);
+  m.def("im2col", &im2col);
+  m.def("col2im", &col2im);
+  m.def("maxpool", &maxpool);
+  m.def("maxpool_bwd", &maxpool_bwd);
+  m.def("avgpool", &avgpool);
+  m.def("avgpool_bwd", &avgpool_bwd);
+  m.def("bn_stats", &bn_stats);
+  m.def("bn_apply", &bn_apply);
+  m.def("bn_bwd_reduce", &bn_bwd_reduce);
+  m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("layernorm_fwd", &layernorm_fwd);
+  m.def("layernorm_bwd", &layernorm_bwd);
+  m.def("softmax_fwd", &softmax_fwd);
+  m.def("softmax_bwd", &softmax_bwd);
+  m.def("softmax_xent", &softmax_xent);
+  m.def("mse", &mse);
+}

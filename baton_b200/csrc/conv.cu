@@ -1,0 +1,264 @@
+// NHWC convolution plumbing around the tcgen05 GEMM: im2col (forward / wgrad operand), col2im
+// (dgrad scatter written as a gather so it needs no atomics), max / average pooling.
+// A convolution is   Y[N*Ho*Wo, Cout] = col[N*Ho*Wo, KH*KW*Cin] * W[Cout, KH*KW*Cin]^T
+// with K index = (kh*KW + kw)*Cin + c, i.e. weights stored [Cout, KH, KW, Cin] (channels_last).
+#include "launch.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int CV_THREADS = 256;
+static inline int cv_grid(long long n, int max_ctas = 148 * 8) {
+  long long g = (n + CV_THREADS - 1) / CV_THREADS;
+  if (g < 1) g = 1;
+  if (g > max_ctas) g = max_ctas;
+  return static_cast<int>(g);
+}
+
+// vector path: C % 8 == 0, one thread per 16-byte chunk of the col matrix
+__global__ void __launch_bounds__(CV_THREADS)
+im2col_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ col, int N, int H, int W, int C8, int KH, int KW,
+                  int stride, int pad, int Ho, int Wo, int kp8) {
+  const long long rows = static_cast<long long>(N) * Ho * Wo;
+  const long long total = rows * kp8;
+  const int k8 = KH * KW * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / kp8;
+    const int kc = static_cast<int>(i - row * kp8);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (kc < k8) {
+      const int tap = kc / C8, c8 = kc - tap * C8;
+      const int kh = tap / KW, kw = tap - kh * KW;
+      const int wo = static_cast<int>(row % Wo);
+      const long long t = row / Wo;
+      const int ho = static_cast<int>(t % Ho);
+      const int n = static_cast<int>(t / Ho);
+      const int h = ho * stride - pad + kh, w = wo * stride - pad + kw;
+      if (h >= 0 && h < H && w >= 0 && w < W)
+        v = __ldg(x + ((static_cast<long long>(n) * H + h) * W + w) * C8 + c8);
+    }
+    col[i] = v;
+  }
+}
+// scalar path (first layer, C = 3)
+__global__ void __launch_bounds__(CV_THREADS)
+im2col_scalar_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W, int C,
+                     int KH, int KW, int stride, int pad, int Ho, int Wo, int kp) {
+  const long long rows = static_cast<long long>(N) * Ho * Wo;
+  const long long total = rows * kp;
+  const int K = KH * KW * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / kp;
+    const int kc = static_cast<int>(i - row * kp);
+    __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+    if (kc < K) {
+      const int tap = kc / C, c = kc - tap * C;
+      const int kh = tap / KW, kw = tap - kh * KW;
+      const int wo = static_cast<int>(row % Wo);
+      const long long t = row / Wo;
+      const int ho = static_cast<int>(t % Ho);
+      const int n = static_cast<int>(t / Ho);
+      const int h = ho * stride - pad + kh, w = wo * stride - pad + kw;
+      if (h >= 0 && h < H && w >= 0 && w < W) v = x[((static_cast<long long>(n) * H + h) * W + w) * C + c];
+    }
+    col[i] = v;
+  }
+}
+
+// dX[n,h,w,c] = sum over taps (kh,kw) with ho = (h + pad - kh)/stride, wo = (w + pad - kw)/stride integral
+// and in range of dcol[(n,ho,wo), (kh*KW+kw)*C + c].  One thread per 8 channels, fp32 accumulation.
+__global__ void __launch_bounds__(CV_THREADS)
+col2im_vec_kernel(const uint4* __restrict__ col, uint4* __restrict__ dx, int N, int H, int W, int C8, int KH, int KW,
+                  int stride, int pad, int Ho, int Wo, int kp8) {
+  const long long total = static_cast<long long>(N) * H * W * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    long long t = i / C8;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int kh = 0; kh < KH; ++kh) {
+      const int hh = h + pad - kh;
+      if (hh < 0 || hh % stride) continue;
+      const int ho = hh / stride;
+      if (ho >= Ho) continue;
+      for (int kw = 0; kw < KW; ++kw) {
+        const int ww = w + pad - kw;
+        if (ww < 0 || ww % stride) continue;
+        const int wo = ww / stride;
+        if (wo >= Wo) continue;
+        const long long row = (static_cast<long long>(n) * Ho + ho) * Wo + wo;
+        const uint4 v = __ldg(col + row * kp8 + (kh * KW + kw) * C8 + c8);
+        const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+      }
+    }
+    dx[i] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                       pack_bf16x2(acc[6], acc[7]));
+  }
+}
+
+// max pooling, NHWC, one thread per (n, ho, wo, channel pair); argmax = flat (h*W + w) of the winner
+__global__ void __launch_bounds__(CV_THREADS)
+maxpool_kernel(const __nv_bfloat162* __restrict__ x, __nv_bfloat162* __restrict__ y, int2* __restrict__ arg, int N,
+               int H, int W, int C2, int k, int stride, int pad, int Ho, int Wo) {
+  const long long total = static_cast<long long>(N) * Ho * Wo * C2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c2 = static_cast<int>(i % C2);
+    long long t = i / C2;
+    const int wo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float m0 = -INFINITY, m1 = -INFINITY;
+    int a0 = -1, a1 = -1;
+    for (int kh = 0; kh < k; ++kh) {
+      const int h = ho * stride - pad + kh;
+      if (h < 0 || h >= H) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int w = wo * stride - pad + kw;
+        if (w < 0 || w >= W) continue;
+        const float2 v = __bfloat1622float2(x[((static_cast<long long>(n) * H + h) * W + w) * C2 + c2]);
+        if (v.x > m0) { m0 = v.x; a0 = h * W + w; }
+        if (v.y > m1) { m1 = v.y; a1 = h * W + w; }
+      }
+    }
+    y[i] = __floats2bfloat162_rn(m0, m1);
+    arg[i] = make_int2(a0, a1);
+  }
+}
+// backward as a gather (no atomics): each input position scans the windows covering it
+__global__ void __launch_bounds__(CV_THREADS)
+maxpool_bwd_gather_kernel(const __nv_bfloat162* __restrict__ dy, const int2* __restrict__ arg,
+                          __nv_bfloat162* __restrict__ dx, int N, int H, int W, int C2, int Ho, int Wo, int k,
+                          int stride, int pad) {
+  const long long total = static_cast<long long>(N) * H * W * C2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c2 = static_cast<int>(i % C2);
+    long long t = i / C2;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    const int me = h * W + w;
+    float g0 = 0.f, g1 = 0.f;
+    for (int kh = 0; kh < k; ++kh) {
+      const int hh = h + pad - kh;
+      if (hh < 0 || hh % stride) continue;
+      const int ho = hh / stride;
+      if (ho >= Ho) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int ww = w + pad - kw;
+        if (ww < 0 || ww % stride) continue;
+        const int wo = ww / stride;
+        if (wo >= Wo) continue;
+        const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C2 + c2;
+        const int2 a = arg[o];
+        const float2 g = __bfloat1622float2(dy[o]);
+        if (a.x == me) g0 += g.x;
+        if (a.y == me) g1 += g.y;
+      }
+    }
+    dx[i] = __floats2bfloat162_rn(g0, g1);
+  }
+}
+
+// global average pool [N, HW, C] -> [N, C] and its backward
+__global__ void __launch_bounds__(CV_THREADS)
+avgpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int HW, int C) {
+  const long long total = static_cast<long long>(N) * C;
+  const float inv = 1.f / HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long n = i / C;
+    float acc = 0.f;
+    for (int p = 0; p < HW; ++p) acc += __bfloat162float(x[(n * HW + p) * C + c]);
+    y[i] = __float2bfloat16_rn(acc * inv);
+  }
+}
+__global__ void __launch_bounds__(CV_THREADS)
+avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int HW, int C) {
+  const long long total = static_cast<long long>(N) * HW * C;
+  const float inv = 1.f / HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long n = i / (static_cast<long long>(HW) * C);
+    dx[i] = __float2bfloat16_rn(__bfloat162float(dy[n * C + c]) * inv);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+#define RET_LAST() return static_cast<int>(cudaGetLastError())
+
+extern "C" int b200_im2col_nhwc(const void* x, void* col, int N, int H, int W, int C, int KH, int KW, int stride,
+                                int pad, int Ho, int Wo, int kp, cudaStream_t stream) {
+  const long long rows = static_cast<long long>(N) * Ho * Wo;
+  if (rows <= 0) return 0;
+  if (C % 8 == 0 && kp % 8 == 0) {
+    im2col_vec_kernel<<<cv_grid(rows * (kp / 8)), CV_THREADS, 0, stream>>>(
+        reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(col), N, H, W, C / 8, KH, KW, stride, pad, Ho, Wo,
+        kp / 8);
+  } else {
+    im2col_scalar_kernel<<<cv_grid(rows * kp), CV_THREADS, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(col), N, H, W, C, KH, KW, stride,
+        pad, Ho, Wo, kp);
+  }
+  RET_LAST();
+}
+extern "C" int b200_col2im_nhwc(const void* col, void* dx, int N, int H, int W, int C, int KH, int KW, int stride,
+                                int pad, int Ho, int Wo, int kp, cudaStream_t stream) {
+  if (C % 8 || kp % 8) return -2;
+  const long long total = static_cast<long long>(N) * H * W * (C / 8);
+  if (total <= 0) return 0;
+  col2im_vec_kernel<<<cv_grid(total), CV_THREADS, 0, stream>>>(reinterpret_cast<const uint4*>(col),
+                                                               reinterpret_cast<uint4*>(dx), N, H, W, C / 8, KH, KW,
+                                                               stride, pad, Ho, Wo, kp / 8);
+  RET_LAST();
+}
+extern "C" int b200_maxpool_nhwc(const void* x, void* y, int* argmax, int N, int H, int W, int C, int k, int stride,
+                                 int pad, int Ho, int Wo, cudaStream_t stream) {
+  if (C % 2) return -2;
+  const long long total = static_cast<long long>(N) * Ho * Wo * (C / 2);
+  if (total <= 0) return 0;
+  maxpool_kernel<<<cv_grid(total), CV_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat162*>(x),
+                                                            reinterpret_cast<__nv_bfloat162*>(y),
+                                                            reinterpret_cast<int2*>(argmax), N, H, W, C / 2, k, stride,
+                                                            pad, Ho, Wo);
+  RET_LAST();
+}
+extern "C" int b200_maxpool_bwd_nhwc(const void* dy, const int* argmax, void* dx, int N, int H, int W, int C, int Ho,
+                                     int Wo, int k, int stride, int pad, cudaStream_t stream) {
+  if (C % 2) return -2;
+  const long long total = static_cast<long long>(N) * H * W * (C / 2);
+  if (total <= 0) return 0;
+  maxpool_bwd_gather_kernel<<<cv_grid(total), CV_THREADS, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat162*>(dy), reinterpret_cast<const int2*>(argmax),
+      reinterpret_cast<__nv_bfloat162*>(dx), N, H, W, C / 2, Ho, Wo, k, stride, pad);
+  RET_LAST();
+}
+extern "C" int b200_avgpool_nhwc(const void* x, void* y, int N, int HW, int C, cudaStream_t stream) {
+  const long long total = static_cast<long long>(N) * C;
+  if (total <= 0) return 0;
+  avgpool_kernel<<<cv_grid(total), CV_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                            reinterpret_cast<__nv_bfloat16*>(y), N, HW, C);
+  RET_LAST();
+}
+extern "C" int b200_avgpool_bwd_nhwc(const void* dy, void* dx, int N, int HW, int C, cudaStream_t stream) {
+  const long long total = static_cast<long long>(N) * HW * C;
+  if (total <= 0) return 0;
+  avgpool_bwd_kernel<<<cv_grid(total), CV_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                                reinterpret_cast<__nv_bfloat16*>(dx), N, HW, C);
+  RET_LAST();
+}

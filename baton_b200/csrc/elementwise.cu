@@ -1,0 +1,354 @@
+// HBM-bound elementwise / reduction kernels over flat buffers: fused arena SGD (K4), multi-source
+// weighted sum (manager-side FedAvg, K1 fallback), casts, batch row gather (K8), column sums
+// (bias gradients), ReLU / GELU pieces.  All use 16-byte vectors and grid-stride loops sized to
+// 148 SMs x a few resident CTAs.
+#include "launch.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+constexpr int EW_THREADS = 256;
+static inline int ew_grid(long long n_vec, int max_ctas = 148 * 8) {
+  long long g = (n_vec + EW_THREADS - 1) / EW_THREADS;
+  if (g < 1) g = 1;
+  if (g > max_ctas) g = max_ctas;
+  return static_cast<int>(g);
+}
+
+// ------------------------------------------------------------------ fused SGD over the arena
+// One pass over {w, g, m}: g' = g + wd*w ; m = mu*m + (1-damp)*g' ; step = nesterov ? g' + mu*m : m ;
+// w -= lr*step ; g = 0 (so split-K wgrad GEMMs can red.add into it next step) ; bf16 shadow = bf16(w).
+// Hyper-parameters come from device memory so a captured CUDA graph can be replayed with a new lr.
+__global__ void __launch_bounds__(EW_THREADS)
+fused_sgd_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ mom,
+                 __nv_bfloat16* __restrict__ wb, long long n, const float* __restrict__ hyper, int zero_grad,
+                 int nesterov) {
+  const float lr = hyper[0], mu = hyper[1], wd = hyper[2], damp = hyper[3];
+  const long long nv = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 wv = reinterpret_cast<float4*>(w)[i];
+    float4 gv = reinterpret_cast<float4*>(g)[i];
+    gv.x = fmaf(wd, wv.x, gv.x); gv.y = fmaf(wd, wv.y, gv.y);
+    gv.z = fmaf(wd, wv.z, gv.z); gv.w = fmaf(wd, wv.w, gv.w);
+    float4 st = gv;
+    if (mom != nullptr) {
+      float4 mv = reinterpret_cast<float4*>(mom)[i];
+      const float od = 1.f - damp;
+      mv.x = fmaf(mu, mv.x, od * gv.x); mv.y = fmaf(mu, mv.y, od * gv.y);
+      mv.z = fmaf(mu, mv.z, od * gv.z); mv.w = fmaf(mu, mv.w, od * gv.w);
+      reinterpret_cast<float4*>(mom)[i] = mv;
+      if (nesterov) {
+        st.x = fmaf(mu, mv.x, gv.x); st.y = fmaf(mu, mv.y, gv.y);
+        st.z = fmaf(mu, mv.z, gv.z); st.w = fmaf(mu, mv.w, gv.w);
+      } else {
+        st = mv;
+      }
+    }
+    wv.x = fmaf(-lr, st.x, wv.x); wv.y = fmaf(-lr, st.y, wv.y);
+    wv.z = fmaf(-lr, st.z, wv.z); wv.w = fmaf(-lr, st.w, wv.w);
+    reinterpret_cast<float4*>(w)[i] = wv;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (wb != nullptr) reinterpret_cast<uint2*>(wb)[i] = make_uint2(pack_bf16x2(wv.x, wv.y), pack_bf16x2(wv.z, wv.w));
+  }
+  // scalar tail (n is normally padded to a multiple of 4 by the arena)
+  if (blockIdx.x == 0) {
+    for (long long i = (nv << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      float gv = fmaf(wd, w[i], g[i]);
+      float st = gv;
+      if (mom != nullptr) {
+        float mv = fmaf(mu, mom[i], (1.f - damp) * gv);
+        mom[i] = mv;
+        st = nesterov ? fmaf(mu, mv, gv) : mv;
+      }
+      float wv = fmaf(-lr, st, w[i]);
+      w[i] = wv;
+      if (zero_grad) g[i] = 0.f;
+      if (wb != nullptr) wb[i] = __float2bfloat16_rn(wv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ multi-source weighted sum
+struct WsumArgs {
+  const void* src[B200_MAX_RANKS];
+  float w[B200_MAX_RANKS];
+  int n_src;
+};
+template <bool BF16>
+__global__ void __launch_bounds__(EW_THREADS) weighted_sum_kernel(void* __restrict__ dst, WsumArgs a, long long n) {
+  constexpr int VEC = BF16 ? 8 : 4;
+  const long long nv = n / VEC;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    for (int k = 0; k < a.n_src; ++k) {
+      const uint4 u = reinterpret_cast<const uint4*>(a.src[k])[i];
+      const float wk = a.w[k];
+      if constexpr (BF16) {
+        const float2 p0 = unpack_bf16x2(u.x), p1 = unpack_bf16x2(u.y), p2 = unpack_bf16x2(u.z), p3 = unpack_bf16x2(u.w);
+        acc[0] = fmaf(wk, p0.x, acc[0]); acc[1] = fmaf(wk, p0.y, acc[1]);
+        acc[2] = fmaf(wk, p1.x, acc[2]); acc[3] = fmaf(wk, p1.y, acc[3]);
+        acc[4] = fmaf(wk, p2.x, acc[4]); acc[5] = fmaf(wk, p2.y, acc[5]);
+        acc[6] = fmaf(wk, p3.x, acc[6]); acc[7] = fmaf(wk, p3.y, acc[7]);
+      } else {
+        acc[0] = fmaf(wk, __uint_as_float(u.x), acc[0]); acc[1] = fmaf(wk, __uint_as_float(u.y), acc[1]);
+        acc[2] = fmaf(wk, __uint_as_float(u.z), acc[2]); acc[3] = fmaf(wk, __uint_as_float(u.w), acc[3]);
+      }
+    }
+    uint4 o;
+    if constexpr (BF16) {
+      o = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                     pack_bf16x2(acc[6], acc[7]));
+    } else {
+      o = make_uint4(__float_as_uint(acc[0]), __float_as_uint(acc[1]), __float_as_uint(acc[2]), __float_as_uint(acc[3]));
+    }
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = nv * VEC + threadIdx.x; i < n; i += blockDim.x) {
+      float acc = 0.f;
+      for (int k = 0; k < a.n_src; ++k) {
+        const float v = BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.src[k])[i])
+                             : reinterpret_cast<const float*>(a.src[k])[i];
+        acc = fmaf(a.w[k], v, acc);
+      }
+      if (BF16)
+        reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(acc);
+      else
+        reinterpret_cast<float*>(dst)[i] = acc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ casts
+__global__ void __launch_bounds__(EW_THREADS) cast_f32_bf16_kernel(const float* __restrict__ s,
+                                                                    __nv_bfloat16* __restrict__ d, long long n) {
+  const long long nv = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(s)[i];
+    reinterpret_cast<uint2*>(d)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (nv << 2) + threadIdx.x; i < n; i += blockDim.x) d[i] = __float2bfloat16_rn(s[i]);
+}
+__global__ void __launch_bounds__(EW_THREADS) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s,
+                                                                    float* __restrict__ d, long long n) {
+  const long long nv = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint2 u = reinterpret_cast<const uint2*>(s)[i];
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    reinterpret_cast<float4*>(d)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (nv << 2) + threadIdx.x; i < n; i += blockDim.x) d[i] = __bfloat162float(s[i]);
+}
+
+// ------------------------------------------------------------------ batch gather (X[idx]) on a resident shard
+__global__ void __launch_bounds__(EW_THREADS)
+gather_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ idx, uint4* __restrict__ dst,
+                   long long n_rows, int row_vecs) {
+  const long long total = n_rows * row_vecs;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / row_vecs;
+    const int c = static_cast<int>(i - r * row_vecs);
+    dst[i] = __ldg(src + idx[r] * row_vecs + c);
+  }
+}
+__global__ void gather_i64_kernel(const long long* __restrict__ src, const long long* __restrict__ idx,
+                                  long long* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = src[idx[i]];
+}
+
+// ------------------------------------------------------------------ column sum of a bf16 [rows, cols] matrix
+// (bias gradient).  Block = 32 x 8: 32 consecutive columns, 8 row lanes; grid.x over column groups,
+// grid.y over row chunks; partial sums are combined with fp32 atomics.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int cols) {
+  __shared__ float s[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (c < cols)
+    for (long long r = static_cast<long long>(blockIdx.y) * 8 + ty; r < rows; r += static_cast<long long>(gridDim.y) * 8)
+      acc += __bfloat162float(x[r * cols + c]);
+  s[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += s[j][tx];
+    atomicAdd(out + c, t);
+  }
+}
+
+// ------------------------------------------------------------------ small bf16 elementwise ops
+__global__ void __launch_bounds__(EW_THREADS)
+add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, long long nv, int relu) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 x = a[i], y = b[i];
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 p = unpack_bf16x2(xs[j]), q = unpack_bf16x2(ys[j]);
+      float u = p.x + q.x, v = p.y + q.y;
+      if (relu) { u = fmaxf(u, 0.f); v = fmaxf(v, 0.f); }
+      r[j] = pack_bf16x2(u, v);
+    }
+    o[i] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+// dx = dy * (y > 0)
+__global__ void __launch_bounds__(EW_THREADS)
+relu_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dy, uint4* __restrict__ dx, long long nv) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 a = y[i], b = dy[i];
+    const uint32_t as[4] = {a.x, a.y, a.z, a.w}, bs[4] = {b.x, b.y, b.z, b.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 p = unpack_bf16x2(as[j]), q = unpack_bf16x2(bs[j]);
+      r[j] = pack_bf16x2(p.x > 0.f ? q.x : 0.f, p.y > 0.f ? q.y : 0.f);
+    }
+    dx[i] = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+__device__ __forceinline__ float gelu_f(float v) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * v * (1.f + tanhf(k0 * (v + k1 * v * v * v)));
+}
+__device__ __forceinline__ float gelu_grad_f(float v) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (v + k1 * v * v * v);
+  const float t = tanhf(u);
+  return 0.5f * (1.f + t) + 0.5f * v * (1.f - t * t) * k0 * (1.f + 3.f * k1 * v * v);
+}
+__global__ void __launch_bounds__(EW_THREADS)
+gelu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = __float2bfloat16_rn(gelu_f(__bfloat162float(x[i])));
+}
+__global__ void __launch_bounds__(EW_THREADS)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                __nv_bfloat16* __restrict__ dx, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * gelu_grad_f(__bfloat162float(x[i])));
+}
+// dst[r, 0:kp] = src[r, 0:k] zero padded (weights whose K is not a multiple of 8, e.g. 7x7x3 = 147)
+__global__ void __launch_bounds__(EW_THREADS)
+pad_rows_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ d, long long rows, int k, int kp) {
+  const long long total = rows * kp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / kp;
+    const int c = static_cast<int>(i - r * kp);
+    d[i] = c < k ? s[r * k + c] : __float2bfloat16_rn(0.f);
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+#define RET_LAST() return static_cast<int>(cudaGetLastError())
+
+extern "C" int b200_fused_sgd(float* w, float* g, float* mom, void* w_bf16, long long n, const float* hyper,
+                              int zero_grad, int nesterov, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  fused_sgd_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, stream>>>(w, g, mom, reinterpret_cast<__nv_bfloat16*>(w_bf16), n,
+                                                                hyper, zero_grad, nesterov);
+  RET_LAST();
+}
+extern "C" int b200_weighted_sum(void* dst, const void* const* srcs, const float* weights, int n_src, long long n,
+                                 int dtype, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (n_src > B200_MAX_RANKS || n_src < 1) return -2;
+  WsumArgs a;
+  a.n_src = n_src;
+  for (int k = 0; k < n_src; ++k) { a.src[k] = srcs[k]; a.w[k] = weights[k]; }
+  if (dtype == 1)
+    weighted_sum_kernel<true><<<ew_grid(n / 8), EW_THREADS, 0, stream>>>(dst, a, n);
+  else
+    weighted_sum_kernel<false><<<ew_grid(n / 4), EW_THREADS, 0, stream>>>(dst, a, n);
+  RET_LAST();
+}
+extern "C" int b200_cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  cast_f32_bf16_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  RET_LAST();
+}
+extern "C" int b200_cast_bf16_f32(const void* src, float* dst, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  cast_bf16_f32_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+  RET_LAST();
+}
+extern "C" int b200_gather_rows(const void* src, const long long* idx, void* dst, long long n_rows,
+                                long long row_bytes, cudaStream_t stream) {
+  if (n_rows <= 0) return 0;
+  if (row_bytes % 16) return -2;
+  const int rv = static_cast<int>(row_bytes / 16);
+  gather_rows_kernel<<<ew_grid(n_rows * rv), EW_THREADS, 0, stream>>>(reinterpret_cast<const uint4*>(src), idx,
+                                                                      reinterpret_cast<uint4*>(dst), n_rows, rv);
+  RET_LAST();
+}
+extern "C" int b200_gather_rows_i64(const long long* src, const long long* idx, long long* dst, long long n,
+                                    cudaStream_t stream) {
+  if (n <= 0) return 0;
+  gather_i64_kernel<<<ew_grid(n, 64), EW_THREADS, 0, stream>>>(src, idx, dst, n);
+  RET_LAST();
+}
+extern "C" int b200_colsum(const void* x, float* out, long long rows, int cols, int accumulate, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * cols, stream);
+  long long gy = (rows + 63) / 64;
+  if (gy > 64) gy = 64;
+  dim3 grid((cols + 31) / 32, static_cast<unsigned>(gy));
+  colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols);
+  RET_LAST();
+}
+extern "C" int b200_add_bf16(const void* a, const void* b, void* out, long long n, int relu, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (n % 8) return -2;
+  add_bf16_kernel<<<ew_grid(n / 8), EW_THREADS, 0, stream>>>(reinterpret_cast<const uint4*>(a),
+                                                             reinterpret_cast<const uint4*>(b),
+                                                             reinterpret_cast<uint4*>(out), n / 8, relu);
+  RET_LAST();
+}
+extern "C" int b200_relu_bwd_bf16(const void* y, const void* dy, void* dx, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (n % 8) return -2;
+  relu_bwd_kernel<<<ew_grid(n / 8), EW_THREADS, 0, stream>>>(reinterpret_cast<const uint4*>(y),
+                                                             reinterpret_cast<const uint4*>(dy),
+                                                             reinterpret_cast<uint4*>(dx), n / 8);
+  RET_LAST();
+}
+extern "C" int b200_gelu_bf16(const void* x, void* y, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  gelu_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                     reinterpret_cast<__nv_bfloat16*>(y), n);
+  RET_LAST();
+}
+extern "C" int b200_gelu_bwd_bf16(const void* x, const void* dy, void* dx, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  gelu_bwd_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+                                                         reinterpret_cast<const __nv_bfloat16*>(dy),
+                                                         reinterpret_cast<__nv_bfloat16*>(dx), n);
+  RET_LAST();
+}
+extern "C" int b200_pad_rows_bf16(const void* src, void* dst, long long rows, int k, int kp, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  pad_rows_kernel<<<ew_grid(rows * kp), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src),
+                                                                 reinterpret_cast<__nv_bfloat16*>(dst), rows, k, kp);
+  RET_LAST();
+}

@@ -1,0 +1,105 @@
+// C launch API of the sm_100a kernels (implemented in the .cu files, wrapped for PyTorch in
+// bindings.cpp).  Every launcher takes raw device pointers and a stream and returns 0 or a
+// CUDA error code, so the .cu files do not include any PyTorch header and compile in seconds.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B200_MAX_RANKS 16
+
+extern "C" {
+
+// ---- gemm_tcgen05.cu
+int b200_gemm_bf16(const void* a, const void* b, void* d, const float* bias, int M, int N, int K, long long lda,
+                   long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act, int split_k, int accumulate,
+                   float alpha, const uint32_t* tile_flags, uint32_t flag_epoch, long long flag_elem_off, int flag_tile_elems,
+                   int force_bn, cudaStream_t stream);
+int b200_gemm_simt(const void* a, const void* b, void* d, const float* bias, int M, int N, int K, long long lda,
+                   long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act, int accumulate,
+                   float alpha, cudaStream_t stream);
+
+// ---- elementwise.cu
+// hyper = device float[4] {lr, momentum, weight_decay, dampening}
+int b200_fused_sgd(float* w, float* g, float* mom, void* w_bf16, long long n, const float* hyper, int zero_grad,
+                   int nesterov, cudaStream_t stream);
+int b200_weighted_sum(void* dst, const void* const* srcs, const float* weights, int n_src, long long n, int dtype,
+                      cudaStream_t stream);  // dtype: 0 fp32, 1 bf16
+int b200_cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
+int b200_cast_bf16_f32(const void* src, float* dst, long long n, cudaStream_t stream);
+int b200_gather_rows(const void* src, const long long* idx, void* dst, long long n_rows, long long row_bytes,
+                     cudaStream_t stream);
+int b200_gather_rows_i64(const long long* src, const long long* idx, long long* dst, long long n,
+                         cudaStream_t stream);
+int b200_colsum(const void* x, float* out, long long rows, int cols, int accumulate, cudaStream_t stream);
+int b200_add_bf16(const void* a, const void* b, void* out, long long n, int relu, cudaStream_t stream);
+int b200_relu_bwd_bf16(const void* y, const void* dy, void* dx, long long n, cudaStream_t stream);
+int b200_gelu_bf16(const void* x, void* y, long long n, cudaStream_t stream);
+int b200_gelu_bwd_bf16(const void* x, const void* dy, void* dx, long long n, cudaStream_t stream);
+int b200_pad_rows_bf16(const void* src, void* dst, long long rows, int k, int kp, cudaStream_t stream);
+
+// ---- fedavg.cu
+struct FedAvgArgs {
+  void* wire[B200_MAX_RANKS];       // peer-mapped wire buffers (index = rank); wire[rank] is local
+  uint32_t* pads[B200_MAX_RANKS];   // peer-mapped signal pads
+  void* wire_mc;                    // multicast address of the wire buffer (NVLS) or nullptr
+  float* theta;                     // local fp32 master weights [n]
+  float* global_w;                  // local fp32 copy of the global model [n] (delta mode) or nullptr
+  void* theta_bf16;                 // local bf16 shadow weights [n] or nullptr
+  float* momentum;                  // optional: momentum buffer to reset at round start (or nullptr)
+  long long* int_local;             // local int64 side arena (num_batches_tracked ...) or nullptr
+  long long* int_wire[B200_MAX_RANKS];  // peer-mapped copies of the int side arena
+  float weights[B200_MAX_RANKS];    // n_k / N per rank (0 = not a participant)
+  uint32_t alive_mask;              // ranks that take part in the collective (readers / receivers)
+  int rank, world;
+  long long n;                      // float elements in the arena
+  int n_int;
+  int wire_bf16;                    // 1: wire dtype bf16, 0: fp32
+  int delta;                        // 1: upload theta - global, result applied as global += sum
+  int use_nvls;                     // 1: multimem.ld_reduce / multimem.st on wire_mc
+  uint32_t epoch;                   // barrier epoch base (this launch uses epoch+1 .. epoch+3)
+  uint32_t* tile_flags;             // optional local per-tile arrival flags (bcast_gemm) or nullptr
+  uint32_t flag_value;              // value published into tile_flags
+  int tile_elems;                   // arena tile size in elements
+  int timeout_cycles_log2;          // spin limit (2^k polls) before the kernel gives up, 0 = none
+  int* status;                      // device int: set non-zero on barrier timeout
+};
+int b200_fedavg_allreduce(const FedAvgArgs* args, int n_ctas, cudaStream_t stream);
+int b200_flag_barrier(uint32_t* const* pads, int rank, int world, uint32_t alive_mask, uint32_t epoch, int slot,
+                      cudaStream_t stream);
+
+// ---- conv.cu
+int b200_im2col_nhwc(const void* x, void* col, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
+                     int Ho, int Wo, int kp, cudaStream_t stream);
+int b200_col2im_nhwc(const void* col, void* dx, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
+                     int Ho, int Wo, int kp, cudaStream_t stream);
+int b200_maxpool_nhwc(const void* x, void* y, int* argmax, int N, int H, int W, int C, int k, int stride, int pad,
+                      int Ho, int Wo, cudaStream_t stream);
+int b200_maxpool_bwd_nhwc(const void* dy, const int* argmax, void* dx, int N, int H, int W, int C, int Ho, int Wo,
+                          int k, int stride, int pad, cudaStream_t stream);
+int b200_avgpool_nhwc(const void* x, void* y, int N, int HW, int C, cudaStream_t stream);
+int b200_avgpool_bwd_nhwc(const void* dy, void* dx, int N, int HW, int C, cudaStream_t stream);
+
+// ---- norm.cu
+int b200_bn_stats(const void* x, float* sums, long long rows, int C, cudaStream_t stream);
+int b200_bn_apply(const void* x, const void* residual, void* y, float* sums, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, float* save_mean, float* save_rstd, long long* nbt,
+                  long long rows, int C, float eps, float momentum, int relu, int training, cudaStream_t stream);
+int b200_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float* save_mean, const float* save_rstd,
+                       float* sums, long long rows, int C, int relu, cudaStream_t stream);
+int b200_bn_bwd_apply(const void* x, const void* y, const void* dy, void* dx, void* dres, const float* gamma,
+                      const float* save_mean, const float* save_rstd, float* sums, float* dgamma, float* dbeta,
+                      long long rows, int C, int relu, cudaStream_t stream);
+int b200_layernorm_fwd(const void* x, const void* residual, void* y, const float* gamma, const float* beta,
+                       float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t stream);
+int b200_layernorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* mean,
+                       const float* rstd, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream);
+int b200_softmax_fwd(const void* x, void* y, long long rows, int C, float scale, cudaStream_t stream);
+int b200_softmax_bwd(const void* y, const void* dy, void* dx, long long rows, int C, float scale,
+                     cudaStream_t stream);
+
+// ---- loss.cu
+int b200_softmax_xent(const void* logits, int logits_fp32, const long long* target, void* dlogits, int dl_fp32,
+                      float* loss_acc, long long rows, int C, long long ld, float grad_scale, cudaStream_t stream);
+int b200_mse(const void* pred, int pred_fp32, const float* target, void* dpred, int dp_fp32, float* loss_acc,
+             long long n, float grad_scale, cudaStream_t stream);
+}

@@ -1,0 +1,432 @@
+// Normalisation kernels (K6): BatchNorm forward/backward over NHWC activations viewed as a
+// [rows, C] bf16 matrix (fused residual add + ReLU, running-stat update), LayerNorm forward /
+// backward (fused residual add) and row softmax for attention.  Statistics and gradients in fp32.
+#include "launch.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ BatchNorm statistics
+// sums[0:C] += sum_r x[r,c] ; sums[C:2C] += sum_r x[r,c]^2.  Block = 32 channel pairs x 8 row lanes.
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const __nv_bfloat162* __restrict__ x, float* __restrict__ sums, long long rows, int C) {
+  __shared__ float s[4][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int C2 = C >> 1;
+  const int c2 = blockIdx.x * 32 + tx;
+  float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+  if (c2 < C2) {
+    for (long long r = static_cast<long long>(blockIdx.y) * 8 + ty; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
+      const float2 v = __bfloat1622float2(x[r * C2 + c2]);
+      a0 += v.x; a1 += v.y;
+      q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+    }
+  }
+  s[0][ty][tx] = a0; s[1][ty][tx] = a1; s[2][ty][tx] = q0; s[3][ty][tx] = q1;
+  __syncthreads();
+  if (ty < 4 && c2 < C2) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += s[ty][j][tx];
+    const int c = c2 * 2 + (ty & 1);
+    atomicAdd(sums + (ty >> 1) * C + c, t);
+  }
+}
+
+// y = relu?( gamma * (x - mean) * rstd + beta + residual? ).  Every block derives per-channel
+// scale/shift from the global sums into shared memory, then streams 16-byte vectors.
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, uint4* __restrict__ y,
+                const float* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ save_mean,
+                float* __restrict__ save_rstd, long long* __restrict__ nbt, long long rows, int C, float eps,
+                float momentum, int relu, int training) {
+  extern __shared__ float sm[];  // scale[C], shift[C]
+  if (training && nbt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;  // num_batches_tracked
+  float* scale = sm;
+  float* shift = sm + C;
+  const float inv_rows = 1.f / static_cast<float>(rows);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, var;
+    if (training) {
+      mean = sums[c] * inv_rows;
+      var = fmaxf(sums[C + c] * inv_rows - mean * mean, 0.f);
+    } else {
+      mean = running_mean[c];
+      var = running_var[c];
+    }
+    const float rstd = rsqrtf(var + eps);
+    const float g = gamma != nullptr ? gamma[c] : 1.f;
+    scale[c] = g * rstd;
+    shift[c] = (beta != nullptr ? beta[c] : 0.f) - mean * g * rstd;
+    if (training && blockIdx.x == 0) {
+      save_mean[c] = mean;
+      save_rstd[c] = rstd;
+      if (running_mean != nullptr) {
+        const float unbiased = rows > 1 ? var * static_cast<float>(rows) / static_cast<float>(rows - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long long total = rows * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % C8) * 8;
+    const uint4 xv = x[i];
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    uint32_t rs[4] = {0u, 0u, 0u, 0u};
+    if (res != nullptr) {
+      const uint4 rv = res[i];
+      rs[0] = rv.x; rs[1] = rv.y; rs[2] = rv.z; rs[3] = rv.w;
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 p = unpack_bf16x2(xs[j]);
+      const float2 q = unpack_bf16x2(rs[j]);
+      float u = fmaf(p.x, scale[c0 + 2 * j], shift[c0 + 2 * j]) + q.x;
+      float v = fmaf(p.y, scale[c0 + 2 * j + 1], shift[c0 + 2 * j + 1]) + q.y;
+      if (relu) { u = fmaxf(u, 0.f); v = fmaxf(v, 0.f); }
+      o[j] = pack_bf16x2(u, v);
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// backward reduce: sums[0:C] += sum dy' ; sums[C:2C] += sum dy' * xhat   with dy' = dy * (y > 0) if relu
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const __nv_bfloat162* __restrict__ x, const __nv_bfloat162* __restrict__ y,
+                     const __nv_bfloat162* __restrict__ dy, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, float* __restrict__ sums, long long rows, int C, int relu) {
+  __shared__ float s[4][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int C2 = C >> 1;
+  const int c2 = blockIdx.x * 32 + tx;
+  float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+  if (c2 < C2) {
+    const float m0 = mean[2 * c2], m1 = mean[2 * c2 + 1], r0 = rstd[2 * c2], r1 = rstd[2 * c2 + 1];
+    for (long long r = static_cast<long long>(blockIdx.y) * 8 + ty; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
+      float2 g = __bfloat1622float2(dy[r * C2 + c2]);
+      if (relu) {
+        const float2 o = __bfloat1622float2(y[r * C2 + c2]);
+        if (!(o.x > 0.f)) g.x = 0.f;
+        if (!(o.y > 0.f)) g.y = 0.f;
+      }
+      const float2 v = __bfloat1622float2(x[r * C2 + c2]);
+      a0 += g.x; a1 += g.y;
+      q0 = fmaf(g.x, (v.x - m0) * r0, q0);
+      q1 = fmaf(g.y, (v.y - m1) * r1, q1);
+    }
+  }
+  s[0][ty][tx] = a0; s[1][ty][tx] = a1; s[2][ty][tx] = q0; s[3][ty][tx] = q1;
+  __syncthreads();
+  if (ty < 4 && c2 < C2) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += s[ty][j][tx];
+    const int c = c2 * 2 + (ty & 1);
+    atomicAdd(sums + (ty >> 1) * C + c, t);
+  }
+}
+
+// dx = gamma * rstd * (dy' - sum_dy/rows - xhat * sum_dy_xhat/rows) ; dres = dy' ;
+// block 0 accumulates dgamma += sum_dy_xhat, dbeta += sum_dy into the fp32 gradient arena.
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy,
+                    uint4* __restrict__ dx, uint4* __restrict__ dres, const float* __restrict__ gamma,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ sums,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C, int relu) {
+  extern __shared__ float sm[];  // a[C], b[C], m[C], r[C]
+  float* ka = sm;
+  float* kb = sm + C;
+  float* km = sm + 2 * C;
+  float* kr = sm + 3 * C;
+  const float inv_rows = 1.f / static_cast<float>(rows);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = gamma != nullptr ? gamma[c] : 1.f;
+    const float r = rstd[c];
+    ka[c] = g * r;                       // multiplies (dy' - mean_dy - xhat * mean_dy_xhat)
+    kb[c] = sums[c] * inv_rows;          // mean_dy
+    km[c] = mean[c];
+    kr[c] = r;
+    if (blockIdx.x == 0) {
+      if (dgamma != nullptr) dgamma[c] += sums[C + c];
+      if (dbeta != nullptr) dbeta[c] += sums[c];
+    }
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long long total = rows * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i % C8) * 8;
+    const uint4 xv = x[i], gv = dy[i];
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+    uint32_t ys[4] = {0u, 0u, 0u, 0u};
+    if (relu) {
+      const uint4 yv = y[i];
+      ys[0] = yv.x; ys[1] = yv.y; ys[2] = yv.z; ys[3] = yv.w;
+    }
+    uint32_t o[4], om[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 p = unpack_bf16x2(xs[j]);
+      float2 g = unpack_bf16x2(gs[j]);
+      if (relu) {
+        const float2 q = unpack_bf16x2(ys[j]);
+        if (!(q.x > 0.f)) g.x = 0.f;
+        if (!(q.y > 0.f)) g.y = 0.f;
+      }
+      om[j] = pack_bf16x2(g.x, g.y);
+      const int ca = c0 + 2 * j, cb = ca + 1;
+      const float xh0 = (p.x - km[ca]) * kr[ca], xh1 = (p.y - km[cb]) * kr[cb];
+      const float d0 = ka[ca] * (g.x - kb[ca] - xh0 * sums[C + ca] * inv_rows);
+      const float d1 = ka[cb] * (g.y - kb[cb] - xh1 * sums[C + cb] * inv_rows);
+      o[j] = pack_bf16x2(d0, d1);
+    }
+    dx[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    if (dres != nullptr) dres[i] = make_uint4(om[0], om[1], om[2], om[3]);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (one warp per row)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+constexpr int LN_MAX_PER_LANE = 32;  // supports C <= 1024 * ... (C / 32 elements per lane, <= 32)
+
+// y = LN(x + residual?) * gamma + beta ; when residual is given the sum is also written to `sum_out`
+// (== y's pre-norm input, needed by backward) -- here we simply recompute it in backward from x+res
+// being stored by the caller, so the kernel only emits y, mean, rstd.
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                     __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     float* __restrict__ mean, float* __restrict__ rstd, long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + row * C;
+  const __nv_bfloat16* rr = res != nullptr ? res + row * C : nullptr;
+  float v[LN_MAX_PER_LANE];
+  float s = 0.f;
+  int cnt = 0;
+  for (int c = lane; c < C; c += 32, ++cnt) {
+    float t = __bfloat162float(xr[c]);
+    if (rr != nullptr) t += __bfloat162float(rr[c]);
+    v[cnt] = t;
+    s += t;
+  }
+  const float mu = warp_sum(s) / C;
+  float q = 0.f;
+  for (int j = 0; j < cnt; ++j) {
+    const float d = v[j] - mu;
+    q = fmaf(d, d, q);
+  }
+  const float rs = rsqrtf(warp_sum(q) / C + eps);
+  __nv_bfloat16* yr = y + row * C;
+  cnt = 0;
+  for (int c = lane; c < C; c += 32, ++cnt)
+    yr[c] = __float2bfloat16_rn((v[cnt] - mu) * rs * gamma[c] + beta[c]);
+  if (lane == 0) {
+    mean[row] = mu;
+    rstd[row] = rs;
+  }
+}
+
+// x here is the pre-norm input (x + residual if a residual was fused in forward).
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                     __nv_bfloat16* __restrict__ dx, const float* __restrict__ gamma, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     long long rows, int C) {
+  extern __shared__ float sm[];  // dgamma[C], dbeta[C] partials of this block
+  float* sg = sm;
+  float* sb = sm + C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { sg[c] = 0.f; sb[c] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  for (long long row = blockIdx.x * static_cast<long long>(warps) + (threadIdx.x >> 5); row < rows;
+       row += static_cast<long long>(gridDim.x) * warps) {
+    const __nv_bfloat16* xr = x + row * C;
+    const __nv_bfloat16* gr = dy + row * C;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[LN_MAX_PER_LANE], gg[LN_MAX_PER_LANE];
+    float s1 = 0.f, s2 = 0.f;
+    int cnt = 0;
+    for (int c = lane; c < C; c += 32, ++cnt) {
+      const float h = (__bfloat162float(xr[c]) - mu) * rs;
+      const float g = __bfloat162float(gr[c]);
+      atomicAdd(sg + c, g * h);
+      atomicAdd(sb + c, g);
+      const float gw = g * gamma[c];
+      xh[cnt] = h; gg[cnt] = gw;
+      s1 += gw; s2 = fmaf(gw, h, s2);
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    __nv_bfloat16* dr = dx + row * C;
+    cnt = 0;
+    for (int c = lane; c < C; c += 32, ++cnt) dr[c] = __float2bfloat16_rn(rs * (gg[cnt] - s1 - xh[cnt] * s2));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(dgamma + c, sg[c]);
+    atomicAdd(dbeta + c, sb[c]);
+  }
+}
+
+// ------------------------------------------------------------------ row softmax (attention probabilities)
+__global__ void __launch_bounds__(256)
+softmax_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows, int C,
+                   float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + row * C;
+  float v[LN_MAX_PER_LANE];
+  float m = -INFINITY;
+  int cnt = 0;
+  for (int c = lane; c < C; c += 32, ++cnt) {
+    v[cnt] = __bfloat162float(xr[c]) * scale;
+    m = fmaxf(m, v[cnt]);
+  }
+  m = warp_max(m);
+  float s = 0.f;
+  for (int j = 0; j < cnt; ++j) {
+    v[j] = __expf(v[j] - m);
+    s += v[j];
+  }
+  const float inv = 1.f / warp_sum(s);
+  __nv_bfloat16* yr = y + row * C;
+  cnt = 0;
+  for (int c = lane; c < C; c += 32, ++cnt) yr[c] = __float2bfloat16_rn(v[cnt] * inv);
+}
+// dx = scale * y * (dy - sum(dy * y))
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
+                   __nv_bfloat16* __restrict__ dx, long long rows, int C, float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* yr = y + row * C;
+  const __nv_bfloat16* gr = dy + row * C;
+  float p[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE];
+  float s = 0.f;
+  int cnt = 0;
+  for (int c = lane; c < C; c += 32, ++cnt) {
+    p[cnt] = __bfloat162float(yr[c]);
+    g[cnt] = __bfloat162float(gr[c]);
+    s = fmaf(p[cnt], g[cnt], s);
+  }
+  s = warp_sum(s);
+  __nv_bfloat16* dr = dx + row * C;
+  cnt = 0;
+  for (int c = lane; c < C; c += 32, ++cnt) dr[c] = __float2bfloat16_rn(scale * p[cnt] * (g[cnt] - s));
+}
+
+static inline dim3 colred_grid(long long rows, int C) {
+  long long gy = (rows + 127) / 128;
+  if (gy > 148) gy = 148;
+  if (gy < 1) gy = 1;
+  return dim3((C / 2 + 31) / 32, static_cast<unsigned>(gy));
+}
+static inline int stream_grid(long long nvec) {
+  long long g = (nvec + 255) / 256;
+  if (g < 1) g = 1;
+  if (g > 148 * 4) g = 148 * 4;
+  return static_cast<int>(g);
+}
+
+}  // namespace b200
+
+using namespace b200;
+#define RET_LAST() return static_cast<int>(cudaGetLastError())
+
+extern "C" int b200_bn_stats(const void* x, float* sums, long long rows, int C, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (C % 2) return -2;
+  bn_stats_kernel<<<colred_grid(rows, C), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat162*>(x), sums, rows, C);
+  RET_LAST();
+}
+extern "C" int b200_bn_apply(const void* x, const void* residual, void* y, float* sums, const float* gamma,
+                             const float* beta, float* running_mean, float* running_var, float* save_mean,
+                             float* save_rstd, long long* nbt, long long rows, int C, float eps, float momentum,
+                             int relu, int training, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (C % 8) return -2;
+  bn_apply_kernel<<<stream_grid(rows * (C / 8)), 256, 2 * C * sizeof(float), stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(residual), reinterpret_cast<uint4*>(y), sums,
+      gamma, beta, running_mean, running_var, save_mean, save_rstd, nbt, rows, C, eps, momentum, relu, training);
+  RET_LAST();
+}
+extern "C" int b200_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float* save_mean,
+                                  const float* save_rstd, float* sums, long long rows, int C, int relu,
+                                  cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (C % 2) return -2;
+  bn_bwd_reduce_kernel<<<colred_grid(rows, C), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat162*>(x), reinterpret_cast<const __nv_bfloat162*>(y),
+      reinterpret_cast<const __nv_bfloat162*>(dy), save_mean, save_rstd, sums, rows, C, relu);
+  RET_LAST();
+}
+extern "C" int b200_bn_bwd_apply(const void* x, const void* y, const void* dy, void* dx, void* dres, const float* gamma,
+                                 const float* save_mean, const float* save_rstd, float* sums, float* dgamma,
+                                 float* dbeta, long long rows, int C, int relu, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (C % 8) return -2;
+  bn_bwd_apply_kernel<<<stream_grid(rows * (C / 8)), 256, 4 * C * sizeof(float), stream>>>(
+      reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(dy),
+      reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dres), gamma, save_mean, save_rstd, sums, dgamma, dbeta,
+      rows, C, relu);
+  RET_LAST();
+}
+extern "C" int b200_layernorm_fwd(const void* x, const void* residual, void* y, const float* gamma, const float* beta,
+                                  float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (C > 32 * LN_MAX_PER_LANE) return -2;
+  const int warps = 8;
+  layernorm_fwd_kernel<<<static_cast<unsigned>((rows + warps - 1) / warps), warps * 32, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(residual),
+      reinterpret_cast<__nv_bfloat16*>(y), gamma, beta, mean, rstd, rows, C, eps);
+  RET_LAST();
+}
+extern "C" int b200_layernorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* mean,
+                                  const float* rstd, float* dgamma, float* dbeta, long long rows, int C,
+                                  cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (C > 32 * LN_MAX_PER_LANE) return -2;
+  long long g = (rows + 7) / 8;
+  if (g > 148 * 2) g = 148 * 2;
+  layernorm_bwd_kernel<<<static_cast<unsigned>(g), 256, 2 * C * sizeof(float), stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy),
+      reinterpret_cast<__nv_bfloat16*>(dx), gamma, mean, rstd, dgamma, dbeta, rows, C);
+  RET_LAST();
+}
+extern "C" int b200_softmax_fwd(const void* x, void* y, long long rows, int C, float scale, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (C > 32 * LN_MAX_PER_LANE) return -2;
+  softmax_fwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), rows, C, scale);
+  RET_LAST();
+}
+extern "C" int b200_softmax_bwd(const void* y, const void* dy, void* dx, long long rows, int C, float scale,
+                                cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  if (C > 32 * LN_MAX_PER_LANE) return -2;
+  softmax_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dy),
+      reinterpret_cast<__nv_bfloat16*>(dx), rows, C, scale);
+  RET_LAST();
+}

@@ -1,0 +1,135 @@
+"""ResNet-18 / ResNet-50 on the sm_100a layers (BASELINE.json configs 2 and 4).
+
+Architecture and ``state_dict`` keys follow the standard ImageNet-style ResNet
+(7x7/2 stem, 3x3/2 max-pool, four stages, global average pool, linear head), so
+a stock PyTorch ResNet ``state_dict`` of the same depth loads unchanged -- the
+"checkpoint layout stays compatible" requirement.  With ``num_classes=10`` the
+ResNet-18 float state is 11,191,242 elements.
+
+Execution differs from a stock model: activations are bf16 NHWC, every
+convolution is im2col + tcgen05 GEMM, BatchNorm fuses the residual add and the
+ReLU of the block, parameters live in the flat arena.  The user-model contract
+(``name``, ``__hash__``, ``train(X, y, n_epoch=...)``) comes from
+``FederatedModule`` (reference demo.py:15-49).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Type
+
+import torch
+from torch import nn
+
+from ..ops import nn as bnn
+from .base import FederatedModule
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: Optional[nn.Module] = None):
+        super().__init__()
+        self.conv1 = bnn.Conv2d(inplanes, planes, 3, stride, 1)
+        self.bn1 = bnn.BatchNorm2d(planes, relu=True)
+        self.conv2 = bnn.Conv2d(planes, planes, 3, 1, 1)
+        self.bn2 = bnn.BatchNorm2d(planes, relu=True)      # relu(bn2(.) + identity), fused
+        self.downsample = downsample
+
+    def forward(self, x):
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.bn1(self.conv1(x))
+        return self.bn2(self.conv2(out), identity)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: Optional[nn.Module] = None):
+        super().__init__()
+        self.conv1 = bnn.Conv2d(inplanes, planes, 1, 1, 0)
+        self.bn1 = bnn.BatchNorm2d(planes, relu=True)
+        self.conv2 = bnn.Conv2d(planes, planes, 3, stride, 1)
+        self.bn2 = bnn.BatchNorm2d(planes, relu=True)
+        self.conv3 = bnn.Conv2d(planes, planes * 4, 1, 1, 0)
+        self.bn3 = bnn.BatchNorm2d(planes * 4, relu=True)
+        self.downsample = downsample
+
+    def forward(self, x):
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.bn1(self.conv1(x))
+        out = self.bn2(self.conv2(out))
+        return self.bn3(self.conv3(out), identity)
+
+
+class _Downsample(nn.Sequential):
+    """``0`` = 1x1 strided conv, ``1`` = BatchNorm (same indices as the stock model)."""
+
+    def __init__(self, inplanes: int, outplanes: int, stride: int):
+        super().__init__(bnn.Conv2d(inplanes, outplanes, 1, stride, 0), bnn.BatchNorm2d(outplanes, relu=False))
+
+
+class ResNet(FederatedModule):
+    loss_kind = "ce"
+    default_lr = 0.05
+    default_batch_size = 128
+
+    def __init__(self, block: Type[nn.Module], layers: Sequence[int], num_classes: int = 1000,
+                 in_channels: int = 3, name: Optional[str] = None):
+        super().__init__()
+        if name:
+            self.name = name
+        self.inplanes = 64
+        self.conv1 = bnn.Conv2d(in_channels, 64, 7, 2, 3)
+        self.bn1 = bnn.BatchNorm2d(64, relu=True)
+        self.maxpool = bnn.MaxPool2d(3, 2, 1)
+        self.layer1 = self._make_layer(block, 64, layers[0], 1)
+        self.layer2 = self._make_layer(block, 128, layers[1], 2)
+        self.layer3 = self._make_layer(block, 256, layers[2], 2)
+        self.layer4 = self._make_layer(block, 512, layers[3], 2)
+        self.avgpool = bnn.GlobalAvgPool()
+        self.fc = bnn.Linear(512 * block.expansion, num_classes, out_fp32=True)
+        self.stats_workspace = None
+        for m in self.modules():   # zero-init the last BN of each block (standard recipe; keeps early training stable)
+            if isinstance(m, BasicBlock):
+                nn.init.zeros_(m.bn2.weight)
+            elif isinstance(m, Bottleneck):
+                nn.init.zeros_(m.bn3.weight)
+
+    def _make_layer(self, block, planes: int, blocks: int, stride: int) -> nn.Sequential:
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = _Downsample(self.inplanes, planes * block.expansion, stride)
+        layers: List[nn.Module] = [block(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes))
+        return nn.Sequential(*layers)
+
+    def forward(self, x):
+        """``x``: NHWC ``[N, H, W, C]`` (bf16 on CUDA)."""
+        x = self.maxpool(self.bn1(self.conv1(x)))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.fc(self.avgpool(x))
+
+    # ------------------------------------------------------------------
+    def build_workspace(self, device) -> torch.Tensor:
+        """One fp32 buffer holding the forward/backward statistic sums of every
+        BatchNorm layer (4*C each), zeroed by ONE memset per training step."""
+        bns = [m for m in self.modules() if isinstance(m, bnn.BatchNorm2d)]
+        total = sum(4 * m.num_features for m in bns)
+        ws = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        for m in bns:
+            m.workspace = ws[off: off + 4 * m.num_features]
+            off += 4 * m.num_features
+        self.stats_workspace = ws
+        return ws
+
+
+def resnet18(num_classes: int = 10, **kw) -> ResNet:
+    kw.setdefault("name", "resnet18")
+    return ResNet(BasicBlock, [2, 2, 2, 2], num_classes=num_classes, **kw)
+
+
+def resnet50(num_classes: int = 1000, **kw) -> ResNet:
+    kw.setdefault("name", "resnet50")
+    return ResNet(Bottleneck, [3, 4, 6, 3], num_classes=num_classes, **kw)

@@ -1,0 +1,235 @@
+"""Functional wrappers over the sm_100a kernels (shape logic + dispatch).
+
+Conventions
+-----------
+* activations are bf16, row-major; images are NHWC (``[N, H, W, C]``);
+* a GEMM operand is a 2-D tensor with unit inner stride; ``*_mn=False`` means the
+  tensor is ``[rows, K]`` (K-major), ``*_mn=True`` means it is ``[K, rows]``
+  (MN-major) -- so forward / dgrad / wgrad need no transposes;
+* kernels that produce parameter gradients *accumulate* into fp32 buffers (the
+  flat gradient arena), the fused SGD step zeroes them again.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from ._ext import load
+
+BF16 = torch.bfloat16
+NUM_SMS = 148
+
+
+def _pitch(t: torch.Tensor) -> int:
+    assert t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1), "GEMM operand must have unit inner stride"
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def _tma_ok(t: torch.Tensor) -> bool:
+    return t.dtype == BF16 and _pitch(t) % 8 == 0 and t.data_ptr() % 16 == 0
+
+
+def pick_bn(M: int, N: int) -> int:
+    """Widest N tile that still yields >= one wave of CTAs; 64 for small problems."""
+    m_tiles = (M + 127) // 128
+    for bn in (256, 128):
+        if N >= bn and m_tiles * ((N + bn - 1) // bn) >= NUM_SMS:
+            return bn
+    if N > 128 and m_tiles * ((N + 127) // 128) >= NUM_SMS // 2:
+        return 128
+    return 64
+
+
+def pick_split_k(M: int, N: int, K: int, bn: int) -> int:
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    k_tiles = (K + 63) // 64
+    if tiles >= NUM_SMS // 2 or k_tiles < 8:
+        return 1
+    return max(1, min(k_tiles // 4, NUM_SMS // tiles))
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
+         out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = BF16, bias: Optional[torch.Tensor] = None,
+         act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: Optional[int] = None,
+         n_valid: Optional[int] = None, flags: Optional[torch.Tensor] = None, flag_epoch: int = 0,
+         flag_elem_off: int = 0, flag_tile_elems: int = 0, force_bn: int = 0, force_simt: bool = False) -> torch.Tensor:
+    """``out[M,N] = act(alpha * A @ B^T + bias)`` on tcgen05 tensor cores.
+
+    ``n_valid`` limits the written columns (used when B carries zero K-padding
+    rows, e.g. the wgrad of a layer whose K was padded to a multiple of 8)."""
+    C = load()
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    assert K == Kb, "GEMM reduction dims differ: {} vs {}".format(K, Kb)
+    if n_valid is not None:
+        N = min(N, n_valid)
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+        if accumulate:
+            out.zero_()
+    ldd = out.stride(0) if out.dim() == 2 else N
+    lda, ldb = _pitch(a), _pitch(b)
+    use_simt = force_simt or not (_tma_ok(a) and _tma_ok(b))
+    if use_simt:
+        C.gemm(a, b, out, bias, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, 1, accumulate, alpha, None, 0, 0, 0, 0, True)
+        return out
+    bn = force_bn or pick_bn(M, N)
+    if split_k is None:
+        split_k = pick_split_k(M, N, K, bn) if (accumulate and out.dtype == torch.float32) else 1
+    if split_k > 1:
+        assert out.dtype == torch.float32 and bias is None and act == 0
+    C.gemm(a, b, out, bias, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, split_k, accumulate, alpha, flags, flag_epoch,
+           flag_elem_off, flag_tile_elems, bn, False)
+    return out
+
+
+# ---------------------------------------------------------------------------- elementwise / optimizer
+def fused_sgd(w: torch.Tensor, g: torch.Tensor, hyper: torch.Tensor, momentum_buf: Optional[torch.Tensor] = None,
+              w_bf16: Optional[torch.Tensor] = None, zero_grad: bool = True, nesterov: bool = False) -> None:
+    """One kernel over the whole flat arena (reference: ``optimizer.step()``, demo.py:47)."""
+    load().fused_sgd(w, g, momentum_buf, w_bf16, hyper, zero_grad, nesterov)
+
+
+def weighted_sum_(dst: torch.Tensor, srcs: Sequence[torch.Tensor], weights: Sequence[float]) -> torch.Tensor:
+    """``dst = sum_k weights[k] * srcs[k]`` in one pass (manager-side FedAvg, manager.py:124-126)."""
+    C = load()
+    flat_dst = dst.view(-1) if dst.is_contiguous() else None
+    if flat_dst is None or dst.dtype not in (torch.float32, BF16) or len(srcs) > C.MAX_RANKS:
+        acc = torch.zeros_like(dst, dtype=torch.float32)
+        for s, w in zip(srcs, weights):
+            acc.add_(s.to(device=dst.device, dtype=torch.float32), alpha=float(w))
+        dst.copy_(acc.to(dst.dtype))
+        return dst
+    ss = [s.to(device=dst.device, dtype=dst.dtype).contiguous().view(-1) for s in srcs]
+    C.weighted_sum(flat_dst, ss, [float(w) for w in weights])
+    return dst
+
+
+def cast(src: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty(src.shape, dtype=dtype, device=src.device)
+    load().cast(src.contiguous(), out)
+    return out
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``src[idx]`` for a resident on-GPU shard (reference: ``X[batch_idxs]``, demo.py:41-42)."""
+    if out is None:
+        out = torch.empty((idx.numel(),) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    load().gather_rows(src, idx, out)
+    return out
+
+
+def colsum_(x2d: torch.Tensor, out: torch.Tensor, accumulate: bool = True) -> torch.Tensor:
+    load().colsum(x2d, out, x2d.shape[0], x2d.shape[1], accumulate)
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor, relu: bool = False) -> torch.Tensor:
+    out = torch.empty_like(a)
+    load().add_bf16(a, b, out, relu)
+    return out
+
+
+def relu_bwd(y: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    dx = torch.empty_like(dy)
+    load().relu_bwd(y, dy, dx)
+    return dx
+
+
+def gelu(x: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(x)
+    load().gelu(x, y)
+    return y
+
+
+def gelu_bwd(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    dx = torch.empty_like(x)
+    load().gelu_bwd(x, dy, dx)
+    return dx
+
+
+def pad_rows(src2d: torch.Tensor, kp: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows, k = src2d.shape
+    if out is None:
+        out = torch.empty((rows, kp), dtype=BF16, device=src2d.device)
+    load().pad_rows(src2d, out, rows, k, kp)
+    return out
+
+
+# ---------------------------------------------------------------------------- conv plumbing
+def conv_out_size(h: int, k: int, stride: int, pad: int) -> int:
+    return (h + 2 * pad - k) // stride + 1
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def im2col(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int) -> Tuple[torch.Tensor, int, int, int]:
+    """NHWC ``x`` -> ``col[N*Ho*Wo, Kp]`` with ``Kp = round_up(kh*kw*C, 8)``."""
+    n, h, w, c = x.shape
+    ho, wo = conv_out_size(h, kh, stride, pad), conv_out_size(w, kw, stride, pad)
+    kp = round_up(kh * kw * c, 8)
+    col = torch.empty((n * ho * wo, kp), dtype=BF16, device=x.device)
+    load().im2col(x, col, n, h, w, c, kh, kw, stride, pad, ho, wo, kp)
+    return col, ho, wo, kp
+
+
+def col2im(col: torch.Tensor, shape: Tuple[int, int, int, int], kh: int, kw: int, stride: int, pad: int,
+           ho: int, wo: int) -> torch.Tensor:
+    n, h, w, c = shape
+    dx = torch.empty(shape, dtype=BF16, device=col.device)
+    load().col2im(col, dx, n, h, w, c, kh, kw, stride, pad, ho, wo, col.shape[1])
+    return dx
+
+
+def maxpool(x: torch.Tensor, k: int, stride: int, pad: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    n, h, w, c = x.shape
+    ho, wo = conv_out_size(h, k, stride, pad), conv_out_size(w, k, stride, pad)
+    y = torch.empty((n, ho, wo, c), dtype=BF16, device=x.device)
+    arg = torch.empty((n, ho, wo, c), dtype=torch.int32, device=x.device)
+    load().maxpool(x, y, arg, n, h, w, c, k, stride, pad, ho, wo)
+    return y, arg
+
+
+def maxpool_bwd(dy: torch.Tensor, arg: torch.Tensor, in_shape, k: int, stride: int, pad: int) -> torch.Tensor:
+    n, h, w, c = in_shape
+    dx = torch.empty(in_shape, dtype=BF16, device=dy.device)
+    load().maxpool_bwd(dy, arg, dx, n, h, w, c, dy.shape[1], dy.shape[2], k, stride, pad)
+    return dx
+
+
+def avgpool(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    y = torch.empty((n, c), dtype=BF16, device=x.device)
+    load().avgpool(x, y, n, h * w, c)
+    return y
+
+
+def avgpool_bwd(dy: torch.Tensor, in_shape) -> torch.Tensor:
+    n, h, w, c = in_shape
+    dx = torch.empty(in_shape, dtype=BF16, device=dy.device)
+    load().avgpool_bwd(dy, dx, n, h * w, c)
+    return dx
+
+
+# ---------------------------------------------------------------------------- losses
+def softmax_xent(logits: torch.Tensor, target: torch.Tensor, want_grad: bool = True,
+                 grad_dtype: Optional[torch.dtype] = None):
+    """Fused softmax cross-entropy: returns ``(acc, dlogits)`` where ``acc[0]`` is the
+    batch-mean loss and ``acc[1]`` the number of correct predictions."""
+    rows, c = logits.shape
+    acc = torch.zeros(2, dtype=torch.float32, device=logits.device)
+    dl = torch.empty_like(logits, dtype=grad_dtype or logits.dtype) if want_grad else None
+    load().softmax_xent(logits, target, dl, acc, rows, c, logits.stride(0), 1.0 / rows)
+    return acc, dl
+
+
+def mse(pred: torch.Tensor, target: torch.Tensor, want_grad: bool = True):
+    acc = torch.zeros(2, dtype=torch.float32, device=pred.device)
+    dp = torch.empty_like(pred) if want_grad else None
+    load().mse(pred.contiguous(), target.contiguous().float(), dp, acc, 1.0 / pred.numel())
+    return acc, dp

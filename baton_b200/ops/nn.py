@@ -1,0 +1,458 @@
+"""Layers built on the sm_100a kernels, with hand-written backward passes.
+
+Every layer keeps an fp32 master parameter (a view into the flat parameter
+arena once ``ParamArena`` has adopted the model) and consumes a bf16 shadow
+copy (``weight_bf16``, a view into the bf16 arena refreshed by the fused SGD
+kernel).  Backward kernels accumulate parameter gradients *directly* into
+``param.grad`` (views of the flat gradient arena) and report ``None`` to
+autograd, so there is no per-parameter accumulate kernel and the optimizer is a
+single pass over the arena.
+
+Layout: activations are bf16 NHWC / ``[rows, features]``.  Conv weights are
+logically ``[Cout, Cin, KH, KW]`` (state_dict compatible with stock PyTorch)
+stored channels_last, i.e. physically ``[Cout, KH, KW, Cin]`` -- exactly the
+K-major B operand of the implicit GEMM.
+
+On a CPU tensor every layer falls back to the equivalent ``torch.nn.functional``
+call so the control plane / tests run on a GPU-less host.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+from torch.nn import functional as TF
+
+from . import functional as F
+from ._ext import load
+
+BF16 = torch.bfloat16
+
+
+def _grad_target(p: Optional[torch.Tensor]):
+    """fp32 gradient buffer to accumulate into (arena view) or None."""
+    if p is None or p.grad is None or p.grad.dtype != torch.float32:
+        return None
+    return p.grad
+
+
+def _shadow(module: nn.Module, name: str, param: torch.Tensor, as2d: bool = True) -> torch.Tensor:
+    """bf16 copy of a parameter.  Arena-adopted modules carry ``<name>_bf16``
+    views that the SGD / FedAvg kernels keep in sync; otherwise cast on the fly."""
+    sh = getattr(module, name + "_bf16", None)
+    if sh is not None:
+        return sh
+    if param.dim() == 4:  # channels_last conv weight -> [Cout, KH*KW*Cin]
+        src = param.detach().permute(0, 2, 3, 1).contiguous()
+        return F.cast(src.view(param.shape[0], -1), BF16)
+    return F.cast(param.detach().contiguous(), BF16)
+
+
+# ================================================================================ Linear
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, w_bf16, act, out_fp32, flags_cfg):
+        x2 = x.reshape(-1, x.shape[-1])
+        kw = {}
+        if flags_cfg is not None:
+            kw = dict(flags=flags_cfg["flags"], flag_epoch=flags_cfg["epoch"], flag_elem_off=flags_cfg["elem_off"],
+                      flag_tile_elems=flags_cfg["tile_elems"], force_bn=128)
+        y = F.gemm(x2, w_bf16, bias=bias, act=act if act != 2 else 0,
+                   out_dtype=torch.float32 if out_fp32 else BF16, **kw)
+        ctx.act = act
+        pre = None
+        if act == 2:  # GELU needs the pre-activation for backward
+            pre = y
+            y = F.gelu(pre)
+        ctx.save_for_backward(x2, w_bf16, y if act == 1 else pre)
+        ctx.weight, ctx.bias = weight, bias
+        ctx.x_shape = x.shape
+        ctx.needs_dx = x.requires_grad
+        return y.view(*x.shape[:-1], w_bf16.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w_bf16, aux = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if dy2.dtype != BF16:
+            dy2 = F.cast(dy2.contiguous(), BF16)
+        elif not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        if ctx.act == 1:
+            dy2 = F.relu_bwd(aux, dy2)
+        elif ctx.act == 2:
+            dy2 = F.gelu_bwd(aux, dy2)
+        weight, bias = ctx.weight, ctx.bias
+        gw = gb = None
+        # wgrad: dW[N, K] += dY^T[N, M] X[M, K]   (both operands MN-major, no transposes)
+        tgt = _grad_target(weight)
+        if tgt is not None:
+            F.gemm(dy2, x2, a_mn=True, b_mn=True, out=tgt.view(weight.shape[0], -1), accumulate=True)
+        else:
+            gw = F.gemm(dy2, x2, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True).view_as(weight)
+        if bias is not None:
+            tb = _grad_target(bias)
+            if tb is not None:
+                F.colsum_(dy2, tb, accumulate=True)
+            else:
+                gb = F.colsum_(dy2, torch.zeros_like(bias, dtype=torch.float32), accumulate=True)
+        dx = None
+        if ctx.needs_dx:
+            # dgrad: dX[M, K] = dY[M, N] W[N, K]   (B = W is MN-major for this product)
+            dx = F.gemm(dy2, w_bf16, b_mn=True).view(ctx.x_shape)
+        return dx, gw, gb, None, None, None, None
+
+
+class Linear(nn.Module):
+    """``y = act(x W^T + b)``; ``act`` in {None, 'relu', 'gelu'} is fused into the GEMM epilogue."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, act: Optional[str] = None,
+                 out_fp32: bool = False):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.act = {None: 0, "relu": 1, "gelu": 2}[act]
+        self.out_fp32 = out_fp32
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+        self.bias = nn.Parameter(torch.empty(out_features)) if bias else None
+        self.flags_cfg = None  # set by FedAvgSession for the first layer (bcast_gemm)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1 / math.sqrt(self.in_features)
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x):
+        if not x.is_cuda:
+            y = TF.linear(x, self.weight.to(x.dtype), None if self.bias is None else self.bias.to(x.dtype))
+            return TF.relu(y) if self.act == 1 else (TF.gelu(y, approximate="tanh") if self.act == 2 else y)
+        if x.dtype != BF16:
+            x = F.cast(x.contiguous(), BF16)
+        cfg, self.flags_cfg = self.flags_cfg, None  # one-shot: only the first GEMM after a round is gated
+        return _LinearFn.apply(x, self.weight, self.bias, _shadow(self, "weight", self.weight), self.act,
+                               self.out_fp32, cfg)
+
+
+# ================================================================================ Conv2d (NHWC, implicit GEMM)
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, w_bf16, kh, kw, stride, pad):
+        n, h, w, c = x.shape
+        cout = w_bf16.shape[0]
+        if kh == 1 and kw == 1 and stride == 1 and pad == 0 and c % 8 == 0:
+            col, ho, wo, kp = x.view(n * h * w, c), h, w, c
+        else:
+            col, ho, wo, kp = F.im2col(x, kh, kw, stride, pad)
+        y = F.gemm(col, w_bf16)
+        ctx.save_for_backward(col, w_bf16)
+        ctx.weight = weight
+        ctx.geom = (n, h, w, c, kh, kw, stride, pad, ho, wo, kp)
+        ctx.needs_dx = x.requires_grad
+        return y.view(n, ho, wo, cout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        col, w_bf16 = ctx.saved_tensors
+        n, h, w, c, kh, kw, stride, pad, ho, wo, kp = ctx.geom
+        cout = w_bf16.shape[0]
+        dy2 = dy.reshape(n * ho * wo, cout)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        weight = ctx.weight
+        k_true = kh * kw * c
+        gw = None
+        tgt = _grad_target(weight)
+        if tgt is not None:
+            # the arena view is channels_last: physical [Cout, KH, KW, Cin] == [Cout, K]
+            out2d = tgt.permute(0, 2, 3, 1).reshape(cout, k_true) if tgt.dim() == 4 else tgt.view(cout, k_true)
+            assert out2d.data_ptr() == tgt.data_ptr(), "conv weight grad must be channels_last in the arena"
+            F.gemm(dy2, col, a_mn=True, b_mn=True, out=out2d, accumulate=True, n_valid=k_true)
+        else:
+            g2 = F.gemm(dy2, col, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True, n_valid=k_true)
+            gw = g2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
+        dx = None
+        if ctx.needs_dx:
+            dcol = F.gemm(dy2, w_bf16, b_mn=True)  # [M, kp]
+            if kh == 1 and kw == 1 and stride == 1 and pad == 0 and c % 8 == 0:
+                dx = dcol.view(n, h, w, c)
+            else:
+                dx = F.col2im(dcol, (n, h, w, c), kh, kw, stride, pad, ho, wo)
+        return dx, gw, None, None, None, None, None
+
+
+class Conv2d(nn.Module):
+    """NHWC convolution (no bias -- every conv in ResNet is followed by BatchNorm)."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: int, stride: int = 1, padding: int = 0):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        w = torch.empty(out_channels, in_channels, kernel_size, kernel_size)
+        nn.init.kaiming_normal_(w, mode="fan_out", nonlinearity="relu")
+        self.weight = nn.Parameter(w.contiguous(memory_format=torch.channels_last))
+        self.k_true = kernel_size * kernel_size * in_channels
+        self.kp = F.round_up(self.k_true, 8)
+
+    def _w_bf16(self):
+        sh = getattr(self, "weight_bf16", None)
+        if sh is None:
+            sh = _shadow(self, "weight", self.weight)
+        sh = sh.view(self.out_channels, self.k_true)
+        if self.kp != self.k_true:  # K not a multiple of 8 (7x7x3 stem): zero-padded copy for TMA
+            sh = F.pad_rows(sh, self.kp)
+        return sh
+
+    def forward(self, x):
+        if not x.is_cuda:
+            y = TF.conv2d(x.permute(0, 3, 1, 2), self.weight.to(x.dtype), None, self.stride, self.padding)
+            return y.permute(0, 2, 3, 1)
+        return _ConvFn.apply(x, self.weight, self._w_bf16(), self.kernel_size, self.kernel_size, self.stride,
+                             self.padding)
+
+
+# ================================================================================ BatchNorm (+residual +ReLU)
+class _BNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, rmean, rvar, nbt, eps, momentum, relu, training, ws):
+        C_ = load()
+        c = x.shape[-1]
+        rows = x.numel() // c
+        y = torch.empty_like(x)
+        if ws is None:
+            ws = torch.zeros(4 * c, dtype=torch.float32, device=x.device)
+        sums_f, sums_b = ws[: 2 * c], ws[2 * c:]
+        save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        save_rstd = torch.empty(c, dtype=torch.float32, device=x.device)
+        if training:
+            C_.bn_stats(x, sums_f, rows, c)
+        C_.bn_apply(x, residual, y, sums_f, gamma, beta, rmean, rvar, save_mean, save_rstd, nbt, rows, c, eps,
+                    momentum, relu, training)
+        ctx.save_for_backward(x, y, save_mean, save_rstd)
+        ctx.gamma, ctx.beta, ctx.sums_b = gamma, beta, sums_b
+        ctx.relu, ctx.has_res, ctx.rows, ctx.c = relu, residual is not None, rows, c
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        C_ = load()
+        x, y, mean, rstd = ctx.saved_tensors
+        if not dy.is_contiguous():
+            dy = dy.contiguous()
+        gamma, beta = ctx.gamma, ctx.beta
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if ctx.has_res else None
+        C_.bn_bwd_reduce(x, y, dy, mean, rstd, ctx.sums_b, ctx.rows, ctx.c, ctx.relu)
+        tg, tb = _grad_target(gamma), _grad_target(beta)
+        gg = gb = None
+        if tg is None:
+            gg = tg = torch.zeros(ctx.c, dtype=torch.float32, device=x.device)
+        if tb is None:
+            gb = tb = torch.zeros(ctx.c, dtype=torch.float32, device=x.device)
+        C_.bn_bwd_apply(x, y, dy, dx, dres, gamma, mean, rstd, ctx.sums_b, tg, tb, ctx.rows, ctx.c, ctx.relu)
+        if ctx.has_res and dres is None:
+            dres = dy
+        return dx, dres, gg, gb, None, None, None, None, None, None, None, None
+
+
+class BatchNorm2d(nn.Module):
+    """BatchNorm over the channel (last) axis of an NHWC tensor with the residual add
+    and ReLU of a ResNet block fused into the same pass:  ``relu(bn(x) + residual)``."""
+
+    def __init__(self, num_features: int, eps: float = 1e-5, momentum: float = 0.1, relu: bool = False):
+        super().__init__()
+        self.num_features, self.eps, self.momentum, self.relu = num_features, eps, momentum, relu
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        self.workspace = None  # [4*C] fp32 slice of the model-wide stats workspace (zeroed once per step)
+
+    def forward(self, x, residual=None):
+        if not x.is_cuda:
+            xn = x.permute(0, 3, 1, 2)
+            y = TF.batch_norm(xn, self.running_mean, self.running_var, self.weight, self.bias, self.training,
+                              self.momentum, self.eps).permute(0, 2, 3, 1)
+            if self.training:
+                self.num_batches_tracked += 1
+            if residual is not None:
+                y = y + residual
+            return TF.relu(y) if self.relu else y
+        ws = self.workspace
+        if ws is None:
+            ws = torch.zeros(4 * self.num_features, dtype=torch.float32, device=x.device)
+        return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
+                           self.num_batches_tracked if self.training else None, self.eps, self.momentum, self.relu,
+                           self.training, ws)
+
+
+# ================================================================================ pooling / misc
+class _MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        y, arg = F.maxpool(x, k, stride, pad)
+        ctx.save_for_backward(arg)
+        ctx.cfg = (tuple(x.shape), k, stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (arg,) = ctx.saved_tensors
+        shape, k, stride, pad = ctx.cfg
+        return F.maxpool_bwd(dy.contiguous(), arg, shape, k, stride, pad), None, None, None
+
+
+class MaxPool2d(nn.Module):
+    def __init__(self, kernel_size: int = 3, stride: int = 2, padding: int = 1):
+        super().__init__()
+        self.k, self.stride, self.pad = kernel_size, stride, padding
+
+    def forward(self, x):
+        if not x.is_cuda:
+            return TF.max_pool2d(x.permute(0, 3, 1, 2), self.k, self.stride, self.pad).permute(0, 2, 3, 1)
+        return _MaxPoolFn.apply(x, self.k, self.stride, self.pad)
+
+
+class _AvgPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return F.avgpool(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return F.avgpool_bwd(dy.contiguous(), ctx.shape)
+
+
+class GlobalAvgPool(nn.Module):
+    """NHWC ``[N,H,W,C] -> [N,C]`` (a view when H = W = 1, the 32x32-input ResNet case)."""
+
+    def forward(self, x):
+        if x.shape[1] == 1 and x.shape[2] == 1:
+            return x.reshape(x.shape[0], x.shape[3])
+        if not x.is_cuda:
+            return x.mean(dim=(1, 2))
+        return _AvgPoolFn.apply(x)
+
+
+# ================================================================================ LayerNorm / GELU / softmax
+class _LNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, eps):
+        C_ = load()
+        c = x.shape[-1]
+        rows = x.numel() // c
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        C_.layernorm_fwd(x, residual, y, gamma, beta, mean, rstd, rows, c, eps)
+        pre = x if residual is None else F.add(x, residual)
+        ctx.save_for_backward(pre, mean, rstd)
+        ctx.gamma, ctx.beta, ctx.has_res, ctx.rows, ctx.c = gamma, beta, residual is not None, rows, c
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        C_ = load()
+        pre, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(pre)
+        tg, tb = _grad_target(ctx.gamma), _grad_target(ctx.beta)
+        gg = gb = None
+        if tg is None:
+            gg = tg = torch.zeros(ctx.c, dtype=torch.float32, device=dy.device)
+        if tb is None:
+            gb = tb = torch.zeros(ctx.c, dtype=torch.float32, device=dy.device)
+        C_.layernorm_bwd(pre, dy, dx, ctx.gamma, mean, rstd, tg, tb, ctx.rows, ctx.c)
+        return dx, (dx if ctx.has_res else None), gg, gb, None
+
+
+class LayerNorm(nn.Module):
+    """``LN(x + residual)`` over the last axis (residual optional)."""
+
+    def __init__(self, normalized_shape: int, eps: float = 1e-12):
+        super().__init__()
+        self.c, self.eps = normalized_shape, eps
+        self.weight = nn.Parameter(torch.ones(normalized_shape))
+        self.bias = nn.Parameter(torch.zeros(normalized_shape))
+
+    def forward(self, x, residual=None):
+        if not x.is_cuda:
+            if residual is not None:
+                x = x + residual
+            return TF.layer_norm(x, (self.c,), self.weight.to(x.dtype), self.bias.to(x.dtype), self.eps)
+        return _LNFn.apply(x.contiguous(), None if residual is None else residual.contiguous(), self.weight,
+                           self.bias, self.eps)
+
+
+class _SoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        c = x.shape[-1]
+        y = torch.empty_like(x)
+        load().softmax_fwd(x, y, x.numel() // c, c, scale)
+        ctx.save_for_backward(y)
+        ctx.scale = scale
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        c = y.shape[-1]
+        dx = torch.empty_like(y)
+        load().softmax_bwd(y, dy.contiguous(), dx, y.numel() // c, c, ctx.scale)
+        return dx, None
+
+
+def softmax(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """``softmax(scale * x)`` over the last axis."""
+    if not x.is_cuda:
+        return torch.softmax(x * scale, dim=-1)
+    return _SoftmaxFn.apply(x.contiguous(), scale)
+
+
+# ================================================================================ losses
+class _XentFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target):
+        acc, dl = F.softmax_xent(logits, target, want_grad=True)
+        ctx.save_for_backward(dl)
+        ctx.mark_non_differentiable(acc)
+        return acc[0].clone(), acc
+
+    @staticmethod
+    def backward(ctx, g, _unused):
+        (dl,) = ctx.saved_tensors
+        return dl * g.to(dl.dtype), None
+
+
+def cross_entropy(logits: torch.Tensor, target: torch.Tensor):
+    """Fused softmax + NLL + gradient.  Returns ``(loss, stats)`` with
+    ``stats = [mean loss, #correct]`` on the device."""
+    if not logits.is_cuda:
+        loss = TF.cross_entropy(logits.float(), target)
+        hits = (logits.argmax(-1) == target).sum().float()
+        return loss, torch.stack([loss.detach(), hits])
+    return _XentFn.apply(logits.contiguous(), target)
+
+
+class _MseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        acc, dp = F.mse(pred, target, want_grad=True)
+        ctx.save_for_backward(dp)
+        return acc[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        (dp,) = ctx.saved_tensors
+        return dp * g.to(dp.dtype), None
+
+
+def mse_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    if not pred.is_cuda:
+        return TF.mse_loss(pred.float(), target.float().reshape(pred.shape))
+    return _MseFn.apply(pred.contiguous(), target.reshape(pred.shape))

@@ -65,3 +65,145 @@ def run_local_sgd(model: nn.Module, X: torch.Tensor, y: torch.Tensor, *, n_epoch
             optimizer.step()
         loss_history.append(batch_iter.loss)
     return loss_history
+
+
+class GraphedLocalSGD:
+    """CUDA local-SGD engine for an arena-adopted model.
+
+    One *epoch* -- ``n // batch_size`` steps of {on-device batch gather, forward,
+    fused loss, hand-written backward, ONE fused SGD kernel over the arena, loss
+    accumulation} -- is captured into a single CUDA graph and replayed once per
+    epoch, so the host issues one launch per epoch and never synchronises inside
+    a round: the per-epoch losses are read back together when the round ends.
+
+    ``model`` must already be adopted by a :class:`~baton_b200.parallel.arena.ParamArena`
+    (``arena``); the engine is what ``FederatedModule.local_train`` dispatches to
+    for CUDA shards (``model._graphed_trainer``).
+    """
+
+    def __init__(self, model: nn.Module, arena, *, loss: str = "ce", nesterov: bool = False,
+                 use_graph: bool = True, input_dtype=torch.bfloat16):
+        from .ops import functional as F
+        from .ops import nn as bnn
+        self.F, self.bnn = F, bnn
+        self.model, self.arena = model, arena
+        self.loss_kind = loss
+        self.nesterov = nesterov
+        self.use_graph = use_graph
+        self.input_dtype = input_dtype
+        dev = arena.device
+        self.device = dev
+        self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.loss_acc = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._graphs = {}           # (n, batch, x_shape, y_shape) -> captured epoch
+        self._hyper_host = None
+        self.n_kernels_per_step = None
+        self.last_stats = {}
+
+    # -------------------------------------------------------------- one SGD step (capturable)
+    def _loss(self, out, yb):
+        if self.loss_kind in ("ce", "cross_entropy"):
+            loss, stats = self.bnn.cross_entropy(out, yb)
+            return loss, stats
+        loss = self.bnn.mse_loss(out, yb)
+        return loss, torch.stack([loss.detach(), torch.zeros_like(loss.detach())])
+
+    def _step(self, X, y, idx):
+        F = self.F
+        xb = F.gather_rows(X, idx)
+        yb = F.gather_rows(y, idx) if y.dtype == torch.int64 and y.dim() == 1 else y.index_select(0, idx)
+        ws = getattr(self.model, "stats_workspace", None)
+        if ws is not None:
+            ws.zero_()
+        out = self.model(xb)
+        loss, stats = self._loss(out, yb)
+        loss.backward()
+        a = self.arena
+        F.fused_sgd(a.theta[: a.n_param], a.grad, self.hyper, a.momentum,
+                    a.theta_bf16[: a.n_param] if a.theta_bf16 is not None else None,
+                    zero_grad=True, nesterov=self.nesterov)
+        self.loss_acc.add_(stats)
+
+    def _set_hyper(self, lr, momentum, weight_decay, dampening=0.0):
+        vals = (float(lr), float(momentum), float(weight_decay), float(dampening))
+        if vals != self._hyper_host:
+            self.hyper.copy_(torch.tensor(vals, dtype=torch.float32))
+            self._hyper_host = vals
+
+    # -------------------------------------------------------------- epoch graph
+    def _capture(self, X, y, n_steps, batch_size):
+        perm = torch.zeros(n_steps * batch_size, dtype=torch.int64, device=self.device)
+        perm.copy_(torch.arange(n_steps * batch_size, device=self.device) % X.shape[0])
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):   # warm-up outside capture (allocator, lazy init, autograd)
+            # hyper lr=0 during warm-up/capture would still move BN statistics; save/restore the state
+            snap = self.arena.theta.clone()
+            snap_i = self.arena.int_arena.clone()
+            snap_m = self.arena.momentum.clone() if self.arena.momentum is not None else None
+            for _ in range(2):
+                self._step(X, y, perm[:batch_size])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for s in range(n_steps):
+                self._step(X, y, perm[s * batch_size:(s + 1) * batch_size])
+        # undo the side effects of warm-up + capture-time execution (capture does not execute,
+        # warm-up did)
+        self.arena.theta.copy_(snap)
+        self.arena.int_arena.copy_(snap_i)
+        if snap_m is not None:
+            self.arena.momentum.copy_(snap_m)
+        self.arena.grad.zero_()
+        self.arena.sync_shadow()
+        self.loss_acc.zero_()
+        return {"graph": graph, "perm": perm, "X": X, "y": y}
+
+    # -------------------------------------------------------------- public
+    @torch.no_grad()
+    def _shuffle_into(self, perm, n, generator=None):
+        perm.copy_(torch.randperm(n, device=self.device)[: perm.numel()])
+
+    def run(self, X, y, n_epoch: int = 1, lr: float = 0.001, batch_size: int = 32, momentum: float = 0.0,
+            weight_decay: float = 0.0, reshuffle_each_epoch: bool = False, **_ignored) -> List[float]:
+        assert X.is_cuda, "GraphedLocalSGD needs a device-resident shard"
+        nn.Module.train(self.model, True)
+        n = X.shape[0]
+        batch_size = min(batch_size, n)
+        n_steps = n // batch_size
+        tail = n - n_steps * batch_size
+        self._set_hyper(lr, momentum, weight_decay)
+        if momentum and self.arena.momentum is None:
+            self.arena.momentum = torch.zeros_like(self.arena.grad)
+        key = (n, batch_size, tuple(X.shape[1:]), tuple(y.shape[1:]), X.data_ptr(), y.data_ptr(), bool(momentum))
+        epoch_losses = torch.zeros(n_epoch, 2, dtype=torch.float32, device=self.device)
+        if self.use_graph:
+            ent = self._graphs.get(key)
+            if ent is None:
+                ent = self._graphs[key] = self._capture(X, y, n_steps, batch_size)
+            perm_full = torch.randperm(n, device=self.device)
+            for e in range(n_epoch):
+                if reshuffle_each_epoch and e > 0:
+                    perm_full = torch.randperm(n, device=self.device)
+                ent["perm"].copy_(perm_full[: n_steps * batch_size])
+                self.loss_acc.zero_()
+                ent["graph"].replay()
+                if tail:
+                    with torch.enable_grad():
+                        self._step(X, y, perm_full[n_steps * batch_size:])
+                epoch_losses[e].copy_(self.loss_acc)
+        else:
+            perm_full = torch.randperm(n, device=self.device)
+            for e in range(n_epoch):
+                if reshuffle_each_epoch and e > 0:
+                    perm_full = torch.randperm(n, device=self.device)
+                self.loss_acc.zero_()
+                for idx in torch.split(perm_full, batch_size):
+                    with torch.enable_grad():
+                        self._step(X, y, idx)
+                epoch_losses[e].copy_(self.loss_acc)
+        steps = n_steps + (1 if tail else 0)
+        host = epoch_losses.tolist()          # the ONLY host read of the round
+        self.last_stats = {"accuracy": [h[1] / n for h in host], "steps_per_epoch": steps}
+        return [h[0] / steps for h in host]

@@ -1,0 +1,297 @@
+"""Kernel-correctness tier: every sm_100a kernel against a plain PyTorch fp32
+reference of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16 = torch.bfloat16
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-6))
+
+
+@pytest.fixture(scope="module")
+def F():
+    from baton_b200.ops import functional
+    return functional
+
+
+@pytest.fixture(scope="module")
+def bnn():
+    from baton_b200.ops import nn
+    return nn
+
+
+# ------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 512, 576), (384, 200, 1000), (100, 64, 72), (1000, 1000, 4096)])
+def test_gemm_tcgen05_all_majors(F, a_mn, b_mn, M, N, K):
+    torch.manual_seed(M + N + K)
+    dev = _dev()
+    if (a_mn and M % 8) or (b_mn and N % 8) or K % 8:
+        pytest.skip("pitch not TMA aligned for this combination")
+    A = torch.randn(M, K, device=dev).to(BF16)
+    B = torch.randn(N, K, device=dev).to(BF16)
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    ref = A.float() @ B.float().t()
+    out = F.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    assert out.shape == (M, N)
+    assert _rel(out, ref) < 2e-3, _rel(out, ref)
+    out16 = F.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+    assert out16.dtype == BF16 and _rel(out16, ref) < 1e-2
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_tile_widths_bias_act(F, bn):
+    torch.manual_seed(bn)
+    dev = _dev()
+    M, N, K = 300, 520, 328
+    A = torch.randn(M, K, device=dev).to(BF16)
+    B = torch.randn(N, K, device=dev).to(BF16)
+    bias = torch.randn(N, device=dev)
+    ref = torch.relu(0.5 * (A.float() @ B.float().t()) + bias)
+    out = F.gemm(A, B, bias=bias, act=1, alpha=0.5, out_dtype=torch.float32, force_bn=bn)
+    assert _rel(out, ref) < 2e-3
+    refg = torch.nn.functional.gelu(A.float() @ B.float().t() + bias, approximate="tanh")
+    outg = F.gemm(A, B, bias=bias, act=2, out_dtype=torch.float32, force_bn=bn)
+    assert _rel(outg, refg) < 2e-3
+
+
+def test_gemm_split_k_accumulate_and_pitched_output(F):
+    torch.manual_seed(1)
+    dev = _dev()
+    M, N, K = 64, 576, 16384          # wgrad-like: few tiles, long K
+    A = torch.randn(K, M, device=dev).to(BF16)     # MN-major operands
+    B = torch.randn(K, N, device=dev).to(BF16)
+    ref = A.float().t() @ B.float()
+    out = torch.zeros(M, N, device=dev)
+    F.gemm(A, B, a_mn=True, b_mn=True, out=out, accumulate=True)
+    assert _rel(out, ref) < 2e-3
+    F.gemm(A, B, a_mn=True, b_mn=True, out=out, accumulate=True, split_k=7)
+    assert _rel(out, 2 * ref) < 2e-3
+    # n_valid + narrower output pitch (conv stem: K padded 147 -> 152)
+    Bp = torch.zeros(K, 152, device=dev, dtype=BF16)
+    Bp[:, :147] = torch.randn(K, 147, device=dev).to(BF16)
+    out2 = torch.zeros(M, 147, device=dev)
+    F.gemm(A, Bp, a_mn=True, b_mn=True, out=out2, accumulate=True, n_valid=147)
+    assert _rel(out2, A.float().t() @ Bp[:, :147].float()) < 2e-3
+
+
+def test_gemm_simt_fallback_small_pitch(F):
+    torch.manual_seed(2)
+    dev = _dev()
+    M, N, K = 256, 10, 512
+    A = torch.randn(M, K, device=dev).to(BF16)
+    W = torch.randn(N, K, device=dev).to(BF16)
+    dy = torch.randn(M, N, device=dev).to(BF16)       # pitch 10 -> not TMA-able
+    dx = F.gemm(dy, W, b_mn=True)
+    assert _rel(dx, dy.float() @ W.float()) < 1e-2
+    dw = F.gemm(dy, A, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True)
+    assert _rel(dw, dy.float().t() @ A.float()) < 2e-3
+    y = F.gemm(A, W, out_dtype=torch.float32)          # tiny N through TMA with OOB rows
+    assert _rel(y, A.float() @ W.float().t()) < 2e-3
+
+
+# ------------------------------------------------------------------ optimizer / elementwise
+@pytest.mark.parametrize("momentum,nesterov,wd", [(0.0, False, 0.0), (0.9, False, 5e-4), (0.9, True, 1e-4)])
+def test_fused_sgd_matches_torch(F, momentum, nesterov, wd):
+    torch.manual_seed(3)
+    dev = _dev()
+    n = 1_000_004
+    w = torch.randn(n, device=dev)
+    ref_p = torch.nn.Parameter(w.clone())
+    opt = torch.optim.SGD([ref_p], lr=0.1, momentum=momentum, nesterov=nesterov, weight_decay=wd)
+    g_all = [torch.randn(n, device=dev) for _ in range(3)]
+    mom = torch.zeros(n, device=dev) if momentum else None
+    wb = torch.zeros(n, device=dev, dtype=BF16)
+    hyper = torch.tensor([0.1, momentum, wd, 0.0], device=dev)
+    for g in g_all:
+        ref_p.grad = g.clone()
+        opt.step()
+        gg = g.clone()
+        F.fused_sgd(w, gg, hyper, mom, wb, zero_grad=True, nesterov=nesterov)
+        assert float(gg.abs().max()) == 0.0
+    assert torch.allclose(w, ref_p.detach(), atol=1e-5, rtol=1e-5)
+    assert torch.equal(wb, w.to(BF16))
+
+
+def test_weighted_sum_cast_gather_colsum(F):
+    torch.manual_seed(4)
+    dev = _dev()
+    srcs = [torch.randn(100_003, device=dev) for _ in range(5)]
+    ws = [0.1, 0.2, 0.3, 0.15, 0.25]
+    dst = torch.empty(100_003, device=dev)
+    F.weighted_sum_(dst, srcs, ws)
+    assert torch.allclose(dst, sum(w * s for w, s in zip(ws, srcs)), atol=1e-5)
+    s16 = [s.to(BF16) for s in srcs]
+    d16 = torch.empty(100_003, device=dev, dtype=BF16)
+    F.weighted_sum_(d16, s16, ws)
+    assert _rel(d16, sum(w * s.float() for w, s in zip(ws, s16))) < 1e-2
+    x = torch.randn(777, 33, device=dev)
+    assert torch.equal(F.cast(x, BF16), x.to(BF16))
+    assert torch.equal(F.cast(x.to(BF16), torch.float32), x.to(BF16).float())
+    X = torch.randn(500, 32, 32, 8, device=dev).to(BF16)
+    idx = torch.randint(0, 500, (64,), device=dev)
+    assert torch.equal(F.gather_rows(X, idx), X[idx])
+    yl = torch.randint(0, 10, (500,), device=dev)
+    assert torch.equal(F.gather_rows(yl, idx), yl[idx])
+    m = torch.randn(3000, 70, device=dev).to(BF16)
+    out = torch.zeros(70, device=dev)
+    F.colsum_(m, out)
+    assert _rel(out, m.float().sum(0)) < 1e-3
+    a, b = torch.randn(4096, device=dev).to(BF16), torch.randn(4096, device=dev).to(BF16)
+    assert torch.equal(F.add(a, b, relu=True), torch.relu(a.float() + b.float()).to(BF16))
+    assert torch.equal(F.relu_bwd(a, b), torch.where(a > 0, b, torch.zeros_like(b)))
+    xg = torch.randn(5000, device=dev).to(BF16)
+    assert _rel(F.gelu(xg), torch.nn.functional.gelu(xg.float(), approximate="tanh")) < 1e-2
+    xr = xg.float().requires_grad_(True)
+    torch.nn.functional.gelu(xr, approximate="tanh").backward(b[:1].float().expand(5000).clone())
+    assert _rel(F.gelu_bwd(xg, b[:1].expand(5000).contiguous()), xr.grad) < 2e-2
+
+
+# ------------------------------------------------------------------ conv plumbing
+@pytest.mark.parametrize("cin,k,stride,pad,h", [(64, 3, 1, 1, 8), (64, 3, 2, 1, 8), (3, 7, 2, 3, 32), (64, 1, 2, 0, 8)])
+def test_conv2d_forward_backward_vs_torch(bnn, cin, k, stride, pad, h):
+    torch.manual_seed(5)
+    dev = _dev()
+    n, cout = 16, 128
+    conv = bnn.Conv2d(cin, cout, k, stride, pad).to(dev)
+    x = torch.randn(n, h, h, cin, device=dev).to(BF16).requires_grad_(cin != 3)
+    y = conv(x)
+    w32 = conv.weight.detach().to(BF16).float().contiguous().requires_grad_(True)
+    x32 = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = torch.nn.functional.conv2d(x32, w32, None, stride, pad)
+    assert y.shape == yr.permute(0, 2, 3, 1).shape
+    assert _rel(y, yr.permute(0, 2, 3, 1)) < 1e-2
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(conv.weight.grad, w32.grad) < 1e-2
+    if cin != 3:
+        assert _rel(x.grad, x32.grad.permute(0, 2, 3, 1)) < 1.5e-2
+
+
+def test_maxpool_avgpool(bnn):
+    torch.manual_seed(6)
+    dev = _dev()
+    x = torch.randn(8, 16, 16, 64, device=dev).to(BF16).requires_grad_(True)
+    y = bnn.MaxPool2d(3, 2, 1)(x)
+    x32 = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = torch.nn.functional.max_pool2d(x32, 3, 2, 1)
+    assert torch.equal(y.float(), yr.permute(0, 2, 3, 1))
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(x.grad, x32.grad.permute(0, 2, 3, 1)) < 1e-2
+    x2 = torch.randn(8, 4, 4, 64, device=dev).to(BF16).requires_grad_(True)
+    y2 = bnn.GlobalAvgPool()(x2)
+    assert _rel(y2, x2.float().mean((1, 2))) < 1e-2
+    y2.backward(torch.ones_like(y2))
+    assert _rel(x2.grad, torch.full_like(x2, 1 / 16).float()) < 1e-2
+
+
+# ------------------------------------------------------------------ normalisation
+@pytest.mark.parametrize("relu,with_res", [(False, False), (True, False), (True, True)])
+def test_batchnorm_fwd_bwd(bnn, relu, with_res):
+    torch.manual_seed(7)
+    dev = _dev()
+    n, h, c = 32, 8, 64
+    bn = bnn.BatchNorm2d(c, relu=relu).to(dev)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    ref = torch.nn.BatchNorm2d(c).to(dev)
+    ref.load_state_dict(bn.state_dict())
+    x = (torch.randn(n, h, h, c, device=dev) * 2 + 0.5).to(BF16).requires_grad_(True)
+    res = torch.randn(n, h, h, c, device=dev).to(BF16).requires_grad_(True) if with_res else None
+    y = bn(x, res)
+    x32 = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = ref(x32)
+    r32 = None
+    if with_res:
+        r32 = res.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+        yr = yr + r32
+    if relu:
+        yr = torch.relu(yr)
+    assert _rel(y, yr.permute(0, 2, 3, 1)) < 1.5e-2
+    assert torch.allclose(bn.running_mean, ref.running_mean, atol=2e-3)
+    assert torch.allclose(bn.running_var, ref.running_var, atol=2e-2, rtol=2e-2)
+    assert int(bn.num_batches_tracked) == 1
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(x.grad, x32.grad.permute(0, 2, 3, 1)) < 3e-2
+    assert _rel(bn.weight.grad, ref.weight.grad) < 3e-2
+    assert _rel(bn.bias.grad, ref.bias.grad) < 3e-2
+    if with_res:
+        assert _rel(res.grad, r32.grad.permute(0, 2, 3, 1)) < 1e-2
+
+
+def test_layernorm_softmax(bnn):
+    torch.manual_seed(8)
+    dev = _dev()
+    rows, c = 512, 768
+    ln = bnn.LayerNorm(c, eps=1e-12).to(dev)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(rows, c, device=dev).to(BF16).requires_grad_(True)
+    r = torch.randn(rows, c, device=dev).to(BF16).requires_grad_(True)
+    y = ln(x, r)
+    x32 = x.detach().float().requires_grad_(True)
+    r32 = r.detach().float().requires_grad_(True)
+    w32, b32 = ln.weight.detach().clone().requires_grad_(True), ln.bias.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm((x32 + r32).to(BF16).float(), (c,), w32, b32, 1e-12)
+    assert _rel(y, yr) < 1.5e-2
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr.backward(dy.float())
+    assert _rel(ln.weight.grad, w32.grad) < 3e-2 and _rel(ln.bias.grad, b32.grad) < 3e-2
+    s = torch.randn(64, 12, 128, 128, device=dev).to(BF16).requires_grad_(True)
+    p = bnn.softmax(s, 0.125)
+    s32 = s.detach().float().requires_grad_(True)
+    pr = torch.softmax(s32 * 0.125, -1)
+    assert _rel(p, pr) < 1e-2
+    g = torch.randn_like(p)
+    p.backward(g)
+    pr.backward(g.float())
+    assert _rel(s.grad, s32.grad) < 3e-2
+
+
+# ------------------------------------------------------------------ losses
+def test_softmax_xent_and_mse(F, bnn):
+    torch.manual_seed(9)
+    dev = _dev()
+    logits = (torch.randn(256, 10, device=dev) * 3).requires_grad_(True)
+    tgt = torch.randint(0, 10, (256,), device=dev)
+    loss, stats = bnn.cross_entropy(logits, tgt)
+    l32 = logits.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(l32, tgt)
+    assert abs(float(loss) - float(ref)) < 1e-4
+    assert int(stats[1]) == int((l32.argmax(-1) == tgt).sum())
+    loss.backward()
+    ref.backward()
+    assert torch.allclose(logits.grad, l32.grad, atol=1e-6)
+    lb = (torch.randn(128, 1000, device=dev) * 2).to(BF16)
+    tb = torch.randint(0, 1000, (128,), device=dev)
+    acc, dl = F.softmax_xent(lb, tb)
+    assert abs(float(acc[0]) - float(torch.nn.functional.cross_entropy(lb.float(), tb))) < 2e-3
+    p = torch.randn(300, 1, device=dev).requires_grad_(True)
+    t = torch.randn(300, 1, device=dev)
+    l = bnn.mse_loss(p, t)
+    p32 = p.detach().clone().requires_grad_(True)
+    lr = torch.nn.functional.mse_loss(p32, t)
+    assert abs(float(l) - float(lr)) < 1e-5
+    l.backward()
+    lr.backward()
+    assert torch.allclose(p.grad, p32.grad, atol=1e-6)
