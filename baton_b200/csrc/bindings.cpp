@@ -144,29 +144,38 @@ void fedavg_allreduce(const std::vector<int64_t>& wire_ptrs, const std::vector<i
                       at::Tensor theta, const std::optional<at::Tensor>& global_w,
                       const std::optional<at::Tensor>& theta_bf16, const std::optional<at::Tensor>& momentum,
                       const std::optional<at::Tensor>& int_local, const std::vector<int64_t>& int_wire_ptrs,
-                      const std::vector<double>& weights, int64_t alive_mask, int64_t rank, int64_t world, bool wire_bf16,
+                      const std::optional<at::Tensor>& loss_local, const std::vector<int64_t>& loss_wire_ptrs,
+                      const std::optional<at::Tensor>& loss_out, const std::vector<double>& n_samples,
+                      bool counts_from_flags, int64_t alive_mask, int64_t rank, int64_t world, bool wire_bf16,
                       bool delta, bool use_nvls, int64_t epoch, const std::optional<at::Tensor>& tile_flags,
                       int64_t flag_value, int64_t tile_elems, int64_t n_ctas, int64_t timeout_log2,
                       const std::optional<at::Tensor>& status) {
   CHECK_CUDA(theta);
   TORCH_CHECK(world <= B200_MAX_RANKS && static_cast<int64_t>(wire_ptrs.size()) == world &&
-              static_cast<int64_t>(pad_ptrs.size()) == world && static_cast<int64_t>(weights.size()) == world);
+              static_cast<int64_t>(pad_ptrs.size()) == world && static_cast<int64_t>(n_samples.size()) == world);
   TORCH_CHECK(theta.scalar_type() == at::kFloat && theta.is_contiguous());
   const c10::cuda::CUDAGuard guard(theta.device());
   FedAvgArgs a = {};
   for (int64_t k = 0; k < world; ++k) {
     a.wire[k] = reinterpret_cast<void*>(wire_ptrs[k]);
-    a.pads[k] = reinterpret_cast<uint32_t*>(pad_ptrs[k]);
-    a.weights[k] = static_cast<float>(weights[k]);
+    a.pads[k] = reinterpret_cast<unsigned long long*>(pad_ptrs[k]);
+    a.n_samples[k] = static_cast<float>(n_samples[k]);
     a.int_wire[k] = k < static_cast<int64_t>(int_wire_ptrs.size()) ? reinterpret_cast<long long*>(int_wire_ptrs[k]) : nullptr;
+    a.loss_wire[k] = k < static_cast<int64_t>(loss_wire_ptrs.size()) ? reinterpret_cast<float*>(loss_wire_ptrs[k]) : nullptr;
   }
   a.wire_mc = reinterpret_cast<void*>(wire_mc);
   a.theta = theta.data_ptr<float>();
   a.global_w = opt_ptr<float>(global_w);
   a.theta_bf16 = opt_ptr<void>(theta_bf16);
   a.momentum = opt_ptr<float>(momentum);
+  a.n_momentum = a.momentum != nullptr ? momentum->numel() : 0;
   a.int_local = opt_ptr<long long>(int_local);
-  a.n_int = (int_local.has_value() && int_local->defined()) ? static_cast<int>(int_local->numel()) : 0;
+  a.n_int = (a.int_local != nullptr && !int_wire_ptrs.empty()) ? static_cast<int>(int_local->numel()) : 0;
+  a.loss_local = opt_ptr<float>(loss_local);
+  a.loss_out = opt_ptr<float>(loss_out);
+  a.n_loss = (a.loss_local != nullptr && !loss_wire_ptrs.empty()) ? static_cast<int>(loss_local->numel()) : 0;
+  a.counts_from_flags = counts_from_flags;
+  a.nvls_prescale = 1.0f;
   a.alive_mask = static_cast<uint32_t>(alive_mask);
   a.rank = static_cast<int>(rank);
   a.world = static_cast<int>(world);
@@ -178,7 +187,7 @@ void fedavg_allreduce(const std::vector<int64_t>& wire_ptrs, const std::vector<i
   a.tile_flags = opt_ptr<uint32_t>(tile_flags);
   a.flag_value = static_cast<uint32_t>(flag_value);
   a.tile_elems = static_cast<int>(tile_elems);
-  a.timeout_cycles_log2 = static_cast<int>(timeout_log2);
+  a.timeout_log2 = static_cast<int>(timeout_log2);
   a.status = opt_ptr<int>(status);
   TORCH_CHECK(!delta || a.global_w != nullptr, "delta mode needs the global copy");
   TORCH_CHECK(!use_nvls || a.wire_mc != nullptr, "NVLS mode needs the multicast address");
@@ -187,8 +196,8 @@ void fedavg_allreduce(const std::vector<int64_t>& wire_ptrs, const std::vector<i
 
 void flag_barrier(const std::vector<int64_t>& pad_ptrs, int64_t rank, int64_t world, int64_t alive_mask, int64_t epoch,
                   int64_t slot) {
-  std::vector<uint32_t*> pads;
-  for (auto p : pad_ptrs) pads.push_back(reinterpret_cast<uint32_t*>(p));
+  std::vector<unsigned long long*> pads;
+  for (auto p : pad_ptrs) pads.push_back(reinterpret_cast<unsigned long long*>(p));
   check(b200_flag_barrier(pads.data(), rank, world, static_cast<uint32_t>(alive_mask), static_cast<uint32_t>(epoch), slot,
                           cur_stream()),
         "flag_barrier");

@@ -1,8 +1,10 @@
 // Fused FedAvg collective over NVLink 5 / NVSwitch -- ONE persistent kernel per round that does
 //
-//   phase 0  pack      wire_r[t]  = cast( w_r * (theta_r[t] - global[t]) )   (delta mode)
-//                                   cast( w_r * theta_r[t] )                 (weights mode)
-//   barrier  (per-CTA flags in peer-mapped signal pads, st.release.sys / ld.acquire.sys)
+//   phase 0  pack      wire_r[t]  = cast( s_r * (theta_r[t] - global[t]) )   (delta mode)
+//                                   cast( s_r * theta_r[t] )                 (weights mode)
+//   barrier  per-CTA 64-bit flags in peer-mapped pads, st.release.sys / ld.acquire.sys; the flag
+//            word carries this client's sample count n_r, so the n_k exchange that FedAvg needs
+//            (weights w_k = n_k / N, reference manager.py:119-126) costs no extra message
 //   phase 1  reduce    owner(t) pulls tile t from every participant with 16 B peer loads over
 //            + bcast   NVLink (or ONE multimem.ld_reduce: the switch adds the replicas), sums in
 //                      fp32 in fixed rank order, casts, and pushes the result into tile t of every
@@ -12,19 +14,22 @@
 //   phase 2  apply     global += result ; theta = global ; bf16 shadow = bf16(theta) ; momentum = 0
 //                      (the reference's load_state_dict, worker.py:98, with no extra pass), then
 //                      publish a per-tile arrival flag so the next forward's first GEMM
-//                      (gemm_tcgen05, flag-gated TMA producer) can start on tile 0 while the rest
-//                      of the arena is still in flight.
+//                      (gemm_tcgen05, flag-gated TMA producer) can start on its weight tiles while
+//                      the rest of the arena is still in flight.
+//   barrier  (closing: wire / pads may be reused by the next round)
 //
 // This replaces the reference's upload (worker.py:108-118), CPU reduce (manager.py:119-126),
 // broadcast (manager.py:77-86) and load_state_dict (worker.py:98).  No NCCL call on this path.
+// The per-epoch loss history is reduced the same way (manager.py:127-130) by CTA 0.
 //
 // Tile t (tile_elems elements) is owned by the (t mod A)-th live rank and handled by CTA
 // ((t div A) mod G) on EVERY rank in every phase, so a per-CTA cross-GPU barrier is enough:
 // CTA b only ever consumes data produced by CTA b of some rank.
 //
-// Participation: weights[k] == 0 -> rank k is not read (P2P) / packs zeros (NVLS);
+// Participation: n_k == 0 -> rank k is not read (P2P) / packs zeros (NVLS);
 // alive_mask bit k == 0 -> rank k is neither read, written nor waited for (dead process), so a
-// dead peer cannot hang the collective the way a blocking NCCL call would.
+// dead peer cannot hang the collective the way a blocking NCCL call would; a bounded spin turns a
+// peer that dies mid-collective into an error status instead of a hang.
 #include "ptx.cuh"
 #include "launch.h"
 
@@ -32,28 +37,41 @@ namespace b200 {
 
 constexpr int FEDAVG_THREADS = 512;
 
-// Per-CTA barrier across the live ranks.  pads[k] is rank k's signal pad (peer-mapped); slot
-// layout: pad[(cta * B200_MAX_RANKS + src_rank)].  Epochs only grow, so no reset races.
-__device__ __forceinline__ bool cta_barrier_all_ranks(const FedAvgArgs& a, uint32_t epoch, int* status) {
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Per-CTA barrier across the live ranks.  pads[k] is rank k's pad (peer-mapped); slot layout
+// pad[cta * B200_MAX_RANKS + src_rank], word = (epoch << 32) | payload.  Epochs only grow, so no
+// reset races.  payload_out[k] (shared memory) receives rank k's payload.
+__device__ __forceinline__ bool cta_barrier_all_ranks(const FedAvgArgs& a, uint32_t epoch, uint32_t payload,
+                                                      uint32_t* payload_out) {
   __syncthreads();
   const int t = threadIdx.x;
   bool ok = true;
   if (t < a.world && ((a.alive_mask >> t) & 1u)) {
     fence_sys();
-    st_release_sys(a.pads[t] + (static_cast<size_t>(blockIdx.x) * B200_MAX_RANKS + a.rank), epoch);
-    const uint32_t* mine = a.pads[a.rank] + (static_cast<size_t>(blockIdx.x) * B200_MAX_RANKS + t);
-    unsigned long long spins = 0;
-    const unsigned long long limit = a.timeout_cycles_log2 > 0 ? (1ull << a.timeout_cycles_log2) : ~0ull;
-    while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
+    const unsigned long long word = (static_cast<unsigned long long>(epoch) << 32) | payload;
+    st_release_sys_u64(a.pads[t] + (static_cast<size_t>(blockIdx.x) * B200_MAX_RANKS + a.rank), word);
+    const unsigned long long* mine = a.pads[a.rank] + (static_cast<size_t>(blockIdx.x) * B200_MAX_RANKS + t);
+    unsigned long long spins = 0, v;
+    const unsigned long long limit = a.timeout_log2 > 0 ? (1ull << a.timeout_log2) : ~0ull;
+    while (static_cast<int32_t>(static_cast<uint32_t>((v = ld_acquire_sys_u64(mine)) >> 32) - epoch) < 0) {
       if (++spins > limit) {
         ok = false;
-        if (status != nullptr) atomicExch(status, 1 + t);
+        if (a.status != nullptr) atomicExch(a.status, 1 + t);
         break;
       }
     }
+    if (payload_out != nullptr) payload_out[t] = static_cast<uint32_t>(v);
   }
-  __syncthreads();
-  return ok;
+  const int all_ok = __syncthreads_and(ok ? 1 : 0);
+  return all_ok != 0;
 }
 
 template <bool WIRE_BF16>
@@ -94,10 +112,13 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(con
   using W = Wire<WIRE_BF16>;
   constexpr int VEC = W::VEC;
   const int G = gridDim.x;
-  // live ranks, in rank order; A = number alive; my position among them
-  __shared__ uint8_t* s_wire[B200_MAX_RANKS];
+  __shared__ uint8_t* s_wire[B200_MAX_RANKS];   // indexed by position among the live ranks
   __shared__ long long* s_int[B200_MAX_RANKS];
+  __shared__ float* s_loss[B200_MAX_RANKS];
+  __shared__ int s_rank[B200_MAX_RANKS];
   __shared__ float s_w[B200_MAX_RANKS];
+  __shared__ uint32_t s_payload[B200_MAX_RANKS];  // indexed by rank
+  __shared__ float s_inv_total;
   int A = 0, my_pos = -1;
   for (int k = 0; k < a.world; ++k)
     if ((a.alive_mask >> k) & 1u) {
@@ -105,53 +126,69 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(con
       if (threadIdx.x == 0) {
         s_wire[A] = reinterpret_cast<uint8_t*>(a.wire[k]);
         s_int[A] = a.int_wire[k];
-        s_w[A] = a.weights[k];
+        s_loss[A] = a.loss_wire[k];
+        s_rank[A] = k;
       }
       ++A;
     }
   if (my_pos < 0 || A == 0) return;
-  __syncthreads();
   const long long n = a.n;
-  const int T = a.tile_elems;  // multiple of VEC * FEDAVG_THREADS is not required; multiple of VEC is
+  const int T = a.tile_elems;
   const long long n_tiles = (n + T - 1) / T;
-  const float my_w = a.weights[a.rank];
+  const float my_n = a.n_samples[a.rank];
   const size_t esz = WIRE_BF16 ? 2 : 4;
   uint8_t* my_wire = reinterpret_cast<uint8_t*>(a.wire[a.rank]);
 
-  // ---------------------------------------------------------------- phase 0: pack + prescale + cast
-  // P2P mode applies the weight on the reader side (full-precision upload); NVLS mode needs the
-  // scaled value on the wire because the switch can only add.
-  const float pack_scale = a.use_nvls ? my_w : 1.0f;
-  if (my_w != 0.f || a.use_nvls) {
-    // same tile -> CTA map as the other phases: CTA b owns q = b, b+G, ... and tiles q*A .. q*A+A-1
-    for (long long t = static_cast<long long>(blockIdx.x) * A; t < n_tiles;
-         t = ((t + 1) % A == 0) ? (t + 1 + static_cast<long long>(G - 1) * A) : (t + 1)) {
-      const long long base = t * T;
-      const int len = static_cast<int>((n - base) < T ? (n - base) : T);
-      for (int i = threadIdx.x * VEC; i < len; i += FEDAVG_THREADS * VEC) {
-        float f[VEC];
+  // ---------------------------------------------------------------- phase 0: pack (+ prescale) + cast
+  // P2P mode applies w_k on the reader side (the upload keeps full wire precision); NVLS mode needs
+  // the scaled value on the wire because the switch can only add: scale by n_k now, by 1/N in phase 2.
+  const float pack_scale = a.use_nvls ? my_n * a.nvls_prescale : 1.0f;
+  if (my_n != 0.f || a.use_nvls) {
+    for (long long q = blockIdx.x; q * A < n_tiles; q += G) {
+      for (int r = 0; r < A; ++r) {
+        const long long t = q * A + r;
+        if (t >= n_tiles) break;
+        const long long base = t * T;
+        const int len = static_cast<int>((n - base) < T ? (n - base) : T);
+        for (int i = threadIdx.x * VEC; i < len; i += FEDAVG_THREADS * VEC) {
+          float f[VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; j += 4) {
-          float4 th = *reinterpret_cast<const float4*>(a.theta + base + i + j);
-          if (a.delta) {
-            float4 g = *reinterpret_cast<const float4*>(a.global_w + base + i + j);
-            th.x -= g.x; th.y -= g.y; th.z -= g.z; th.w -= g.w;
+          for (int j = 0; j < VEC; j += 4) {
+            float4 th = *reinterpret_cast<const float4*>(a.theta + base + i + j);
+            if (a.delta) {
+              const float4 g = *reinterpret_cast<const float4*>(a.global_w + base + i + j);
+              th.x -= g.x; th.y -= g.y; th.z -= g.z; th.w -= g.w;
+            }
+            f[j] = th.x * pack_scale; f[j + 1] = th.y * pack_scale;
+            f[j + 2] = th.z * pack_scale; f[j + 3] = th.w * pack_scale;
           }
-          f[j] = th.x * pack_scale; f[j + 1] = th.y * pack_scale;
-          f[j + 2] = th.z * pack_scale; f[j + 3] = th.w * pack_scale;
+          *reinterpret_cast<uint4*>(my_wire + (base + i) * esz) = W::pack(f);
         }
-        *reinterpret_cast<uint4*>(my_wire + (base + i) * esz) = W::pack(f);
       }
     }
   }
-  // integer side arena (num_batches_tracked ...): publish the local values
-  if (a.n_int > 0 && blockIdx.x == 0) {
+  if (blockIdx.x == 0) {
+    // integer side arena (num_batches_tracked ...) and the local per-epoch losses
     for (int i = threadIdx.x; i < a.n_int; i += FEDAVG_THREADS) a.int_wire[a.rank][i] = a.int_local[i];
+    for (int i = threadIdx.x; i < a.n_loss; i += FEDAVG_THREADS) a.loss_wire[a.rank][i] = a.loss_local[i];
   }
-  if (!cta_barrier_all_ranks(a, a.epoch + 1, a.status)) return;
+  if (!cta_barrier_all_ranks(a, a.epoch + 1, __float_as_uint(my_n), s_payload)) return;
+
+  // weights w_k = n_k / N from the counts that rode on the barrier flags (or the host's plan)
+  if (threadIdx.x == 0) {
+    float total = 0.f;
+    for (int k = 0; k < A; ++k) {
+      const float nk = a.counts_from_flags ? __uint_as_float(s_payload[s_rank[k]]) : a.n_samples[s_rank[k]];
+      s_w[k] = nk;
+      total += nk;
+    }
+    const float inv = total > 0.f ? 1.f / total : 0.f;
+    for (int k = 0; k < A; ++k) s_w[k] *= inv;
+    s_inv_total = inv;
+  }
+  __syncthreads();
 
   // ---------------------------------------------------------------- phase 1: reduce + broadcast
-  // tile t belongs to live rank alive[t % A]; on that rank CTA ((t / A) % G) handles it
   for (long long t = my_pos + static_cast<long long>(blockIdx.x) * A; t < n_tiles; t += static_cast<long long>(G) * A) {
     const long long base = t * T;
     const int len = static_cast<int>((n - base) < T ? (n - base) : T);
@@ -159,15 +196,15 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(con
       const size_t off = (base + i) * esz;
       uint4 out;
       if (a.use_nvls) {
-        out = W::mc_reduce(reinterpret_cast<const uint8_t*>(a.wire_mc) + off);  // switch adds the replicas
-        multimem_st_v4(reinterpret_cast<uint8_t*>(a.wire_mc) + off, out);       // switch replicates the store
+        out = W::mc_reduce(reinterpret_cast<const uint8_t*>(a.wire_mc) + off);  // the switch adds the replicas
+        multimem_st_v4(reinterpret_cast<uint8_t*>(a.wire_mc) + off, out);       // the switch replicates the store
       } else {
-        // issue all peer loads first (MLP), then accumulate in fixed rank order (deterministic)
+        // issue all peer loads first (memory-level parallelism), then accumulate in fixed rank
+        // order so the result is bitwise identical on every run
         uint4 v[B200_MAX_RANKS];
 #pragma unroll
-        for (int k = 0; k < B200_MAX_RANKS; ++k) {
+        for (int k = 0; k < B200_MAX_RANKS; ++k)
           if (k < A && s_w[k] != 0.f) v[k] = ld_volatile_v4(s_wire[k] + off);
-        }
         float acc[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
@@ -185,16 +222,25 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(con
         }
         out = W::pack(acc);
 #pragma unroll
-        for (int k = 0; k < B200_MAX_RANKS; ++k) {
+        for (int k = 0; k < B200_MAX_RANKS; ++k)
           if (k < A) st_na_v4(s_wire[k] + off, out);
-        }
       }
     }
   }
-  if (!cta_barrier_all_ranks(a, a.epoch + 2, a.status)) return;
+  // weighted per-epoch loss (manager.py:127-130); every rank computes the same tiny vector
+  if (blockIdx.x == 0 && a.loss_out != nullptr) {
+    for (int e = threadIdx.x; e < a.n_loss; e += FEDAVG_THREADS) {
+      float acc = 0.f;
+      for (int k = 0; k < A; ++k)
+        if (s_w[k] != 0.f) acc = fmaf(s_w[k], *reinterpret_cast<volatile float*>(s_loss[k] + e), acc);
+      a.loss_out[e] = acc;
+    }
+  }
+  if (!cta_barrier_all_ranks(a, a.epoch + 2, 0u, nullptr)) return;
 
   // ---------------------------------------------------------------- phase 2: running-mean apply
   // CTA b applies exactly the tiles CTA b of the owners produced: (t / A) % G == b
+  const float apply_scale = a.use_nvls ? s_inv_total / a.nvls_prescale : 1.0f;
   for (long long q = blockIdx.x; q * A < n_tiles; q += G) {
     for (int r = 0; r < A; ++r) {
       const long long t = q * A + r;
@@ -206,20 +252,18 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(con
         W::unpack(ld_volatile_v4(my_wire + (base + i) * esz), f);
 #pragma unroll
         for (int j = 0; j < VEC; j += 4) {
-          float4 nw;
+          float4 nw = make_float4(f[j] * apply_scale, f[j + 1] * apply_scale, f[j + 2] * apply_scale,
+                                  f[j + 3] * apply_scale);
           if (a.delta) {
-            float4 g = *reinterpret_cast<const float4*>(a.global_w + base + i + j);
-            nw = make_float4(g.x + f[j], g.y + f[j + 1], g.z + f[j + 2], g.w + f[j + 3]);
-            *reinterpret_cast<float4*>(a.global_w + base + i + j) = nw;
-          } else {
-            nw = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            if (a.global_w != nullptr) *reinterpret_cast<float4*>(a.global_w + base + i + j) = nw;
+            const float4 g = *reinterpret_cast<const float4*>(a.global_w + base + i + j);
+            nw.x += g.x; nw.y += g.y; nw.z += g.z; nw.w += g.w;
           }
+          if (a.global_w != nullptr) *reinterpret_cast<float4*>(a.global_w + base + i + j) = nw;
           *reinterpret_cast<float4*>(a.theta + base + i + j) = nw;
-          if (a.momentum != nullptr)
+          if (a.momentum != nullptr && base + i + j < a.n_momentum)
             *reinterpret_cast<float4*>(a.momentum + base + i + j) = make_float4(0.f, 0.f, 0.f, 0.f);
           if (a.theta_bf16 != nullptr) {
-            uint2 o = make_uint2(pack_bf16x2(nw.x, nw.y), pack_bf16x2(nw.z, nw.w));
+            const uint2 o = make_uint2(pack_bf16x2(nw.x, nw.y), pack_bf16x2(nw.z, nw.w));
             *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.theta_bf16) + (base + i + j) * 2) = o;
           }
         }
@@ -239,25 +283,26 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(con
       long long m = a.int_local[i];
       for (int k = 0; k < A; ++k)
         if (s_w[k] != 0.f) {
-          long long v = *reinterpret_cast<volatile long long*>(s_int[k] + i);
+          const long long v = *reinterpret_cast<volatile long long*>(s_int[k] + i);
           m = v > m ? v : m;
         }
       a.int_local[i] = m;
     }
   }
   // closing barrier: nobody may start the next round's phase 0 (overwriting its wire buffer, which
-  // peers pushed results into) or exit and let the host reuse int_wire while a peer still reads it
-  cta_barrier_all_ranks(a, a.epoch + 3, a.status);
+  // peers pushed results into) or reuse int/loss wire pages while a peer still reads them
+  cta_barrier_all_ranks(a, a.epoch + 3, 0u, nullptr);
 }
 
-// stand-alone cross-GPU barrier on the signal pads (one CTA): used to fence host-side phases
+// stand-alone cross-GPU barrier on the pads (one CTA): fences host-side phases
 __global__ void flag_barrier_kernel(FedAvgArgs a, int slot) {
   const int t = threadIdx.x;
   if (t < a.world && ((a.alive_mask >> t) & 1u)) {
     fence_sys();
-    st_release_sys(a.pads[t] + (static_cast<size_t>(slot) * B200_MAX_RANKS + a.rank), a.epoch);
-    const uint32_t* mine = a.pads[a.rank] + (static_cast<size_t>(slot) * B200_MAX_RANKS + t);
-    while (static_cast<int32_t>(ld_acquire_sys(mine) - a.epoch) < 0) {
+    st_release_sys_u64(a.pads[t] + (static_cast<size_t>(slot) * B200_MAX_RANKS + a.rank),
+                       static_cast<unsigned long long>(a.epoch) << 32);
+    const unsigned long long* mine = a.pads[a.rank] + (static_cast<size_t>(slot) * B200_MAX_RANKS + t);
+    while (static_cast<int32_t>(static_cast<uint32_t>(ld_acquire_sys_u64(mine) >> 32) - a.epoch) < 0) {
     }
   }
 }
@@ -275,8 +320,8 @@ extern "C" int b200_fedavg_allreduce(const FedAvgArgs* args, int n_ctas, cudaStr
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int b200_flag_barrier(uint32_t* const* pads, int rank, int world, uint32_t alive_mask, uint32_t epoch,
-                                 int slot, cudaStream_t stream) {
+extern "C" int b200_flag_barrier(unsigned long long* const* pads, int rank, int world, uint32_t alive_mask,
+                                 uint32_t epoch, int slot, cudaStream_t stream) {
   using namespace b200;
   if (world > B200_MAX_RANKS) return -2;
   FedAvgArgs a = {};

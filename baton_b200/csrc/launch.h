@@ -40,15 +40,22 @@ int b200_pad_rows_bf16(const void* src, void* dst, long long rows, int k, int kp
 // ---- fedavg.cu
 struct FedAvgArgs {
   void* wire[B200_MAX_RANKS];       // peer-mapped wire buffers (index = rank); wire[rank] is local
-  uint32_t* pads[B200_MAX_RANKS];   // peer-mapped signal pads
+  unsigned long long* pads[B200_MAX_RANKS];  // peer-mapped 64-bit barrier pads: (epoch << 32) | payload
   void* wire_mc;                    // multicast address of the wire buffer (NVLS) or nullptr
   float* theta;                     // local fp32 master weights [n]
-  float* global_w;                  // local fp32 copy of the global model [n] (delta mode) or nullptr
+  float* global_w;                  // local fp32 copy of the global model [n] (needed in delta mode)
   void* theta_bf16;                 // local bf16 shadow weights [n] or nullptr
-  float* momentum;                  // optional: momentum buffer to reset at round start (or nullptr)
+  float* momentum;                  // optional: momentum buffer [n_momentum] reset when the round ends
+  long long n_momentum;
   long long* int_local;             // local int64 side arena (num_batches_tracked ...) or nullptr
   long long* int_wire[B200_MAX_RANKS];  // peer-mapped copies of the int side arena
-  float weights[B200_MAX_RANKS];    // n_k / N per rank (0 = not a participant)
+  float* loss_local;                // local per-epoch losses [n_loss] or nullptr
+  float* loss_wire[B200_MAX_RANKS]; // peer-mapped per-epoch loss pages
+  float* loss_out;                  // local: sample-weighted per-epoch loss of the round [n_loss]
+  int n_loss;
+  float n_samples[B200_MAX_RANKS];  // n_k per rank (0 = not a participant); [rank] is always valid
+  int counts_from_flags;            // 1: peers' n_k ride on the barrier flags (no host exchange)
+  float nvls_prescale;              // NVLS: wire = n_k * prescale * x, applied as sum / (N * prescale)
   uint32_t alive_mask;              // ranks that take part in the collective (readers / receivers)
   int rank, world;
   long long n;                      // float elements in the arena
@@ -60,12 +67,12 @@ struct FedAvgArgs {
   uint32_t* tile_flags;             // optional local per-tile arrival flags (bcast_gemm) or nullptr
   uint32_t flag_value;              // value published into tile_flags
   int tile_elems;                   // arena tile size in elements
-  int timeout_cycles_log2;          // spin limit (2^k polls) before the kernel gives up, 0 = none
+  int timeout_log2;                 // spin limit (2^k polls) before the kernel gives up, 0 = none
   int* status;                      // device int: set non-zero on barrier timeout
 };
 int b200_fedavg_allreduce(const FedAvgArgs* args, int n_ctas, cudaStream_t stream);
-int b200_flag_barrier(uint32_t* const* pads, int rank, int world, uint32_t alive_mask, uint32_t epoch, int slot,
-                      cudaStream_t stream);
+int b200_flag_barrier(unsigned long long* const* pads, int rank, int world, uint32_t alive_mask, uint32_t epoch,
+                      int slot, cudaStream_t stream);
 
 // ---- conv.cu
 int b200_im2col_nhwc(const void* x, void* col, int N, int H, int W, int C, int KH, int KW, int stride, int pad,

@@ -4,20 +4,51 @@ The extension is the product: on a machine with a CUDA device every op in
 ``baton_b200.ops`` runs its hand-written kernel and a missing/unloadable
 extension is a hard error (no silent eager fallback).  On a GPU-less host the
 module still imports (``nvcc`` cross-compiles there) but is never called.
+
+``load()`` returns a thin proxy that counts kernel launches per entry point
+(``launch_counts()``); the counts taken while a CUDA graph is being captured are
+what ``bench.py`` multiplies out to report ``gpu_launches``.
 """
 from __future__ import annotations
 
 import importlib
 import os
+from collections import Counter
 
-_C = None
-_ERR = None
+_RAW = None
+_PROXY = None
+_COUNTS: Counter = Counter()
+
+# entry points that enqueue more than one kernel/memset node
+_EXTRA_NODES = {"colsum": 1}
+
+
+class _Counting:
+    """Attribute proxy over the pybind module: every call bumps a per-op counter."""
+
+    def __init__(self, mod):
+        object.__setattr__(self, "_mod", mod)
+        object.__setattr__(self, "_cache", {})
+
+    def __getattr__(self, name):
+        cache = object.__getattribute__(self, "_cache")
+        fn = cache.get(name)
+        if fn is None:
+            target = getattr(object.__getattribute__(self, "_mod"), name)
+            if callable(target):
+                def fn(*a, __t=target, __n=name, **k):
+                    _COUNTS[__n] += 1
+                    return __t(*a, **k)
+            else:
+                fn = target
+            cache[name] = fn
+        return fn
 
 
 def load(build_if_missing: bool = False):
-    global _C, _ERR
-    if _C is not None:
-        return _C
+    global _RAW, _PROXY
+    if _PROXY is not None:
+        return _PROXY
     import torch  # noqa: F401  (libtorch must be loaded before the extension)
     here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     so = os.path.join(here, "_C.so")
@@ -25,13 +56,13 @@ def load(build_if_missing: bool = False):
         from .. import build_ext
         build_ext.build()
     try:
-        _C = importlib.import_module("baton_b200._C")
+        _RAW = importlib.import_module("baton_b200._C")
     except Exception as exc:  # pragma: no cover - exercised only on broken installs
-        _ERR = exc
         raise RuntimeError(
             "baton_b200._C (sm_100a kernels) is not available: {!r}. "
             "Run `python -m baton_b200.build_ext`.".format(exc)) from exc
-    return _C
+    _PROXY = _Counting(_RAW)
+    return _PROXY
 
 
 def available() -> bool:
@@ -40,3 +71,12 @@ def available() -> bool:
         return True
     except Exception:
         return False
+
+
+def launch_counts() -> Counter:
+    """Kernel launches issued through the extension since import, by entry point."""
+    return Counter(_COUNTS)
+
+
+def total_launches() -> int:
+    return sum(v + _EXTRA_NODES.get(k, 0) * v for k, v in _COUNTS.items())

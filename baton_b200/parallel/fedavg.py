@@ -1,0 +1,227 @@
+"""The fused NVLink FedAvg data plane (host side).
+
+``FedAvgSession`` owns the symmetric wire buffer of one rank and launches the
+single-kernel round-end collective (``csrc/fedavg.cu``): pack/cast -> weighted
+reduce over peer memory -> broadcast -> running-mean apply into the fp32 master,
+the bf16 shadow and (optionally) per-tile arrival flags that gate the first GEMM
+of the next forward (``bcast_gemm``).
+
+It replaces, for GPU-seated clients, the reference's upload (worker.py:108-118),
+the manager's CPU reduce (manager.py:119-126), the broadcast (manager.py:77-86)
+and ``load_state_dict`` (worker.py:98).  ``NcclSession`` implements the same
+interface with ``torch.distributed`` collectives: it is the BASELINE the fused
+kernel is measured against and the oracle the tests compare with -- not the
+product path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from .arena import ParamArena
+from .symm import SymmetricBuffer
+
+MAX_LOSS = 64       # per-epoch loss slots carried through the collective
+MAX_CTAS = 148
+
+
+def _align(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+class FedAvgSession:
+    def __init__(self, arena: ParamArena, group=None, *, wire_dtype: str = "bf16", mode: str = "delta",
+                 nvls: "bool | str" = "auto", n_ctas: int = 64, tile_elems: int = 4096, timeout_log2: int = 0,
+                 reset_momentum: bool = True, tile_flags: bool = False):
+        from ..ops._ext import load
+        self._C = load()
+        assert wire_dtype in ("bf16", "fp32") and mode in ("delta", "weights")
+        self.arena = arena
+        self.device = arena.device
+        self.group = group
+        self.wire_bf16 = wire_dtype == "bf16"
+        self.delta = mode == "delta"
+        self.n_ctas = max(1, min(int(n_ctas), MAX_CTAS))
+        self.tile_elems = int(tile_elems)
+        self.timeout_log2 = int(timeout_log2)
+        self.reset_momentum = reset_momentum
+        esz = 2 if self.wire_bf16 else 4
+        self.off_wire = 0
+        self.off_int = _align(arena.n * esz, 256)
+        self.off_loss = _align(self.off_int + max(arena.n_int, 1) * 8, 256)
+        self.off_pads = _align(self.off_loss + MAX_LOSS * 4, 256)
+        total = _align(self.off_pads + (MAX_CTAS + 8) * self._C.MAX_RANKS * 8, 2 << 20)
+        self.symm = SymmetricBuffer(total, self.device, group)
+        self.rank, self.world = self.symm.rank, self.symm.world
+        assert self.world <= self._C.MAX_RANKS
+        self.use_nvls = self.symm.has_multicast if nvls == "auto" else (bool(nvls) and self.symm.has_multicast)
+        self.epoch = 0
+        self.rounds = 0
+        self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.loss_local = torch.zeros(MAX_LOSS, dtype=torch.float32, device=self.device)
+        self.loss_out = torch.zeros(MAX_LOSS, dtype=torch.float32, device=self.device)
+        n_tiles = (arena.n + self.tile_elems - 1) // self.tile_elems
+        self.tile_flags = torch.zeros(n_tiles, dtype=torch.int32, device=self.device) if tile_flags else None
+        # a high-priority stream lets the collective's CTAs become resident ahead of a flag-gated
+        # GEMM that is launched right behind it on the compute stream
+        self.stream = torch.cuda.Stream(device=self.device, priority=-1) if self.device.type == "cuda" else None
+        self.symm.barrier()
+
+    # ------------------------------------------------------------------ the collective
+    def aggregate(self, n_samples_by_rank: Optional[Sequence[float]] = None,
+                  alive_ranks: Optional[Sequence[int]] = None, my_n: Optional[float] = None,
+                  loss_history: Optional[Sequence[float]] = None, on_side_stream: bool = False) -> None:
+        """Launch the fused reduce+broadcast+apply.  Either the full per-rank sample
+        counts are given (manager-driven rounds: the plan comes over HTTP) or only this
+        rank's own count ``my_n`` (SPMD engine: peers' counts ride on the barrier flags)."""
+        world = self.world
+        if n_samples_by_rank is not None:
+            counts = [float(x) for x in n_samples_by_rank] + [0.0] * (world - len(n_samples_by_rank))
+            counts = counts[:world]
+            from_flags = False
+        else:
+            assert my_n is not None
+            counts = [0.0] * world
+            counts[self.rank] = float(my_n)
+            from_flags = True
+        alive = list(range(world)) if alive_ranks is None else [int(r) for r in alive_ranks if 0 <= int(r) < world]
+        if self.rank not in alive:
+            return  # this seat is not part of the round (it keeps its stale replica)
+        mask = 0
+        for r in alive:
+            mask |= 1 << r
+        if loss_history is not None:
+            k = min(len(loss_history), MAX_LOSS)
+            self.loss_local.zero_()
+            self.loss_local[:k].copy_(torch.tensor([float(x) for x in loss_history[:k]]), non_blocking=True)
+        a = self.arena
+        flag_value = self.rounds + 1
+        cur = torch.cuda.current_stream(self.device)
+        stream = self.stream if on_side_stream else cur
+        if on_side_stream:
+            stream.wait_stream(cur)
+        with torch.cuda.stream(stream):
+            self._C.fedavg_allreduce(
+                self.symm.peer_ptrs(self.off_wire), self.symm.peer_ptrs(self.off_pads),
+                self.symm.mc(self.off_wire) if self.use_nvls else 0,
+                a.theta, a.global_w, a.theta_bf16,
+                a.momentum if self.reset_momentum else None,
+                a.int_arena if a.n_int > 0 else None,
+                self.symm.peer_ptrs(self.off_int) if a.n_int > 0 else [],
+                self.loss_local, self.symm.peer_ptrs(self.off_loss), self.loss_out,
+                counts, from_flags, mask, self.rank, world, self.wire_bf16, self.delta,
+                bool(self.use_nvls and len(alive) == world), self.epoch,
+                self.tile_flags, flag_value, self.tile_elems, self.n_ctas, self.timeout_log2, self.status)
+        self.epoch = (self.epoch + 3) & 0x7FFFFFFF
+        self.rounds += 1
+        self._side_pending = on_side_stream
+
+    def join(self) -> None:
+        """Make the compute stream wait for a side-stream collective."""
+        if getattr(self, "_side_pending", False):
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+            self._side_pending = False
+
+    def gate_first_layer(self, module, slot_name: Optional[str] = None) -> None:
+        """bcast_gemm: make the NEXT forward of ``module`` (an ``ops.nn.Linear`` whose
+        weight is the first GEMM operand of the model) wait, tile by tile, on the arrival
+        flags this round's collective publishes, instead of on the whole kernel."""
+        if self.tile_flags is None:
+            raise RuntimeError("session was created with tile_flags=False")
+        slot = None
+        for name, s in self.arena.slots.items():
+            if slot_name is not None and name == slot_name:
+                slot = s
+                break
+            if slot_name is None and s.is_param and len(s.shape) == 2:
+                owner = self.arena._owner(name)
+                if owner is module:
+                    slot = s
+                    break
+        if slot is None:
+            raise ValueError("module weight not found in the arena")
+        module.flags_cfg = {"flags": self.tile_flags, "epoch": self.rounds, "elem_off": slot.offset,
+                            "tile_elems": self.tile_elems}
+
+    def reduced_loss(self, n_epoch: int) -> List[float]:
+        return self.loss_out[: min(n_epoch, MAX_LOSS)].tolist()
+
+    def check(self) -> None:
+        code = int(self.status.item())
+        if code:
+            self.status.zero_()
+            raise RuntimeError("FedAvg collective timed out waiting for rank {}".format(code - 1))
+
+    def wire_bytes(self) -> int:
+        return self.arena.n * (2 if self.wire_bf16 else 4)
+
+
+class NcclSession:
+    """Same contract through ``torch.distributed`` collectives (baseline / oracle)."""
+
+    def __init__(self, arena: ParamArena, group=None, *, wire_dtype: str = "bf16", mode: str = "delta",
+                 reset_momentum: bool = True, **_unused):
+        import torch.distributed as dist
+        self.dist = dist
+        self.arena, self.group, self.device = arena, group, arena.device
+        self.wire_dtype = torch.bfloat16 if wire_dtype == "bf16" else torch.float32
+        self.delta = mode == "delta"
+        self.reset_momentum = reset_momentum
+        inited = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if inited else 1
+        self.rank = dist.get_rank(group) if inited else 0
+        self.wire = torch.zeros(arena.n, dtype=self.wire_dtype, device=self.device)
+        self.counts = torch.zeros(self.world, dtype=torch.float32, device=self.device)
+        self.loss_buf = torch.zeros(MAX_LOSS, dtype=torch.float32, device=self.device)
+        self.loss_out = torch.zeros(MAX_LOSS, dtype=torch.float32, device=self.device)
+        self.rounds = 0
+
+    @torch.no_grad()
+    def aggregate(self, n_samples_by_rank=None, alive_ranks=None, my_n=None, loss_history=None, **_unused) -> None:
+        a, dist = self.arena, self.dist
+        if n_samples_by_rank is not None:
+            counts = torch.tensor([float(x) for x in n_samples_by_rank][: self.world], device=self.device)
+        else:
+            self.counts.zero_()
+            self.counts[self.rank] = float(my_n)
+            if self.world > 1:
+                dist.all_reduce(self.counts, group=self.group)
+            counts = self.counts
+        total = counts.sum()
+        w = counts[self.rank] / total
+        src = (a.theta - a.global_w) if self.delta else a.theta
+        self.wire.copy_((src * w).to(self.wire_dtype))
+        if self.world > 1:
+            dist.all_reduce(self.wire, group=self.group)
+        if loss_history is not None:
+            k = min(len(loss_history), MAX_LOSS)
+            self.loss_buf.zero_()
+            self.loss_buf[:k] = torch.tensor([float(x) for x in loss_history[:k]], device=self.device) * w
+            if self.world > 1:
+                dist.all_reduce(self.loss_buf, group=self.group)
+            self.loss_out.copy_(self.loss_buf)
+        if self.delta:
+            a.global_w.add_(self.wire.float())
+        else:
+            a.global_w.copy_(self.wire.float())
+        a.theta.copy_(a.global_w)
+        if a.theta_bf16 is not None:
+            a.theta_bf16.copy_(a.theta.to(torch.bfloat16))
+        if a.n_int > 0 and self.world > 1:
+            dist.all_reduce(a.int_arena, op=dist.ReduceOp.MAX, group=self.group)
+        if self.reset_momentum and a.momentum is not None:
+            a.momentum.zero_()
+        self.rounds += 1
+
+    def join(self) -> None:
+        pass
+
+    def reduced_loss(self, n_epoch: int) -> List[float]:
+        return self.loss_out[: min(n_epoch, MAX_LOSS)].tolist()
+
+    def check(self) -> None:
+        pass
+
+    def wire_bytes(self) -> int:
+        return self.arena.n * (2 if self.wire_dtype == torch.bfloat16 else 4)

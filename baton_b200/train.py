@@ -145,10 +145,14 @@ class GraphedLocalSGD:
                 self._step(X, y, perm[:batch_size])
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        from .ops._ext import total_launches
         graph = torch.cuda.CUDAGraph()
+        c0 = total_launches()
         with torch.cuda.graph(graph):
             for s in range(n_steps):
                 self._step(X, y, perm[s * batch_size:(s + 1) * batch_size])
+        self.kernels_per_epoch = total_launches() - c0      # our kernels inside one epoch graph
+        self.n_kernels_per_step = self.kernels_per_epoch // max(1, n_steps)
         # undo the side effects of warm-up + capture-time execution (capture does not execute,
         # warm-up did)
         self.arena.theta.copy_(snap)
@@ -166,7 +170,8 @@ class GraphedLocalSGD:
         perm.copy_(torch.randperm(n, device=self.device)[: perm.numel()])
 
     def run(self, X, y, n_epoch: int = 1, lr: float = 0.001, batch_size: int = 32, momentum: float = 0.0,
-            weight_decay: float = 0.0, reshuffle_each_epoch: bool = False, **_ignored) -> List[float]:
+            weight_decay: float = 0.0, reshuffle_each_epoch: bool = False, return_device: bool = False,
+            **_ignored):
         assert X.is_cuda, "GraphedLocalSGD needs a device-resident shard"
         nn.Module.train(self.model, True)
         n = X.shape[0]
@@ -204,6 +209,9 @@ class GraphedLocalSGD:
                         self._step(X, y, idx)
                 epoch_losses[e].copy_(self.loss_acc)
         steps = n_steps + (1 if tail else 0)
+        self.last_steps = steps
+        if return_device:                     # caller reads (or forwards) the losses itself: no host sync here
+            return epoch_losses
         host = epoch_losses.tolist()          # the ONLY host read of the round
         self.last_stats = {"accuracy": [h[1] / n for h in host], "steps_per_epoch": steps}
         return [h[0] / steps for h in host]
