@@ -41,6 +41,7 @@ struct GemmParams {
   uint32_t flag_epoch;         // value a flag must reach before the data under it may be loaded
   long long flag_elem_off;     // arena element offset of B[0,0]
   int flag_tile_elems;         // arena elements covered by one flag
+  long long flag_bias_off;     // arena element offset of bias[0], or -1
   long long ldb;               // row pitch of B (elements)
   float alpha;
 };
@@ -118,7 +119,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           while (ld_acquire_sys(p.tile_flags + t) < p.flag_epoch) {
           }
         }
-        fence_proxy_async();  // order the acquires before the async-proxy (TMA) reads
+        if (p.flag_bias_off >= 0) {  // the bias slice the epilogue of this CTA will add
+          const long long b0 = p.flag_bias_off + n0, b1 = p.flag_bias_off + n0 + rows_here - 1;
+          for (long long t = b0 / p.flag_tile_elems; t <= b1 / p.flag_tile_elems; ++t) {
+            while (ld_acquire_sys(p.tile_flags + t) < p.flag_epoch) {
+            }
+          }
+        }
+        fence_proxy_async_all();  // order the acquires before the async-proxy (TMA) reads of global memory
       }
       for (int i = 0; i < num_kt; ++i) {
         const int s = i % STAGES;
@@ -191,7 +199,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float x = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias != nullptr && (col0 + j) < p.N) x += __ldg(p.bias + col0 + j);
+        if (p.bias != nullptr && (col0 + j) < p.N) x += p.bias[col0 + j];
         v[j] = apply_act(x, p.act);
       }
       const bool full = (col0 + 32 <= p.N);
@@ -299,7 +307,8 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
                               long long lda, long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act,
                               int split_k, int accumulate, float alpha, const uint32_t* tile_flags,
                               uint32_t flag_epoch,
-                              long long flag_elem_off, int flag_tile_elems, int force_bn, cudaStream_t stream) {
+                              long long flag_elem_off, int flag_tile_elems, long long flag_bias_off, int force_bn,
+                              cudaStream_t stream) {
   using namespace b200;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
@@ -329,6 +338,7 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
   p.a_mn = a_mn; p.b_mn = b_mn; p.k_tiles_per_split = per; p.atomic_out = (split_k > 1 || accumulate) ? 1 : 0;
   p.tile_flags = tile_flags; p.flag_epoch = flag_epoch; p.alpha = alpha;
   p.flag_elem_off = flag_elem_off; p.flag_tile_elems = flag_tile_elems; p.ldb = ldb;
+  p.flag_bias_off = (tile_flags != nullptr && bias != nullptr) ? flag_bias_off : -1;
   if (p.atomic_out && (!out_fp32 || bias != nullptr || act != 0)) return -3;
   dim3 grid((N + bn - 1) / bn, (M + BM - 1) / BM, split_k);
   if (bn == 256) return launch_cfg<256, 4>(ta, tb, p, grid, stream);

@@ -13,7 +13,7 @@ extern "C" {
 int b200_gemm_bf16(const void* a, const void* b, void* d, const float* bias, int M, int N, int K, long long lda,
                    long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act, int split_k, int accumulate,
                    float alpha, const uint32_t* tile_flags, uint32_t flag_epoch, long long flag_elem_off, int flag_tile_elems,
-                   int force_bn, cudaStream_t stream);
+                   long long flag_bias_off, int force_bn, cudaStream_t stream);
 int b200_gemm_simt(const void* a, const void* b, void* d, const float* bias, int M, int N, int K, long long lda,
                    long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act, int accumulate,
                    float alpha, cudaStream_t stream);

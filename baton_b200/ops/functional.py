@@ -54,7 +54,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = BF16, bias: Optional[torch.Tensor] = None,
          act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: Optional[int] = None,
          n_valid: Optional[int] = None, flags: Optional[torch.Tensor] = None, flag_epoch: int = 0,
-         flag_elem_off: int = 0, flag_tile_elems: int = 0, force_bn: int = 0, force_simt: bool = False) -> torch.Tensor:
+         flag_elem_off: int = 0, flag_tile_elems: int = 0, flag_bias_off: int = -1, force_bn: int = 0,
+         force_simt: bool = False) -> torch.Tensor:
     """``out[M,N] = act(alpha * A @ B^T + bias)`` on tcgen05 tensor cores.
 
     ``n_valid`` limits the written columns (used when B carries zero K-padding
@@ -73,7 +74,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     lda, ldb = _pitch(a), _pitch(b)
     use_simt = force_simt or not (_tma_ok(a) and _tma_ok(b))
     if use_simt:
-        C.gemm(a, b, out, bias, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, 1, accumulate, alpha, None, 0, 0, 0, 0, True)
+        C.gemm(a, b, out, bias, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, 1, accumulate, alpha, None, 0, 0, 0, -1, 0,
+               True)
         return out
     bn = force_bn or pick_bn(M, N)
     if split_k is None:
@@ -81,7 +83,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if split_k > 1:
         assert out.dtype == torch.float32 and bias is None and act == 0
     C.gemm(a, b, out, bias, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, split_k, accumulate, alpha, flags, flag_epoch,
-           flag_elem_off, flag_tile_elems, bn, False)
+           flag_elem_off, flag_tile_elems, flag_bias_off, bn, False)
     return out
 
 

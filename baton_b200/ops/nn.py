@@ -58,7 +58,8 @@ class _LinearFn(torch.autograd.Function):
         kw = {}
         if flags_cfg is not None:
             kw = dict(flags=flags_cfg["flags"], flag_epoch=flags_cfg["epoch"], flag_elem_off=flags_cfg["elem_off"],
-                      flag_tile_elems=flags_cfg["tile_elems"], force_bn=128)
+                      flag_tile_elems=flags_cfg["tile_elems"], flag_bias_off=flags_cfg.get("bias_off", -1),
+                      force_bn=128)
         y = F.gemm(x2, w_bf16, bias=bias, act=act if act != 2 else 0,
                    out_dtype=torch.float32 if out_fp32 else BF16, **kw)
         ctx.act = act

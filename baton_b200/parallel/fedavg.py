@@ -141,8 +141,13 @@ class FedAvgSession:
                     break
         if slot is None:
             raise ValueError("module weight not found in the arena")
+        bias_off = -1
+        if getattr(module, "bias", None) is not None:
+            for name, s in self.arena.slots.items():
+                if s.is_param and self.arena._owner(name) is module and name.endswith(".bias"):
+                    bias_off = s.offset
         module.flags_cfg = {"flags": self.tile_flags, "epoch": self.rounds, "elem_off": slot.offset,
-                            "tile_elems": self.tile_elems}
+                            "tile_elems": self.tile_elems, "bias_off": bias_off}
 
     def reduced_loss(self, n_epoch: int) -> List[float]:
         return self.loss_out[: min(n_epoch, MAX_LOSS)].tolist()
