@@ -3,6 +3,7 @@
 // A convolution is   Y[N*Ho*Wo, Cout] = col[N*Ho*Wo, KH*KW*Cin] * W[Cout, KH*KW*Cin]^T
 // with K index = (kh*KW + kw)*Cin + c, i.e. weights stored [Cout, KH, KW, Cin] (channels_last).
 #include "launch.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -19,6 +20,8 @@ static inline int cv_grid(long long n, int max_ctas = 148 * 8) {
 __global__ void __launch_bounds__(CV_THREADS)
 im2col_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ col, int N, int H, int W, int C8, int KH, int KW,
                   int stride, int pad, int Ho, int Wo, int kp8) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long rows = static_cast<long long>(N) * Ho * Wo;
   const long long total = rows * kp8;
   const int k8 = KH * KW * C8;
@@ -45,6 +48,8 @@ im2col_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ col, int N, i
 __global__ void __launch_bounds__(CV_THREADS)
 im2col_scalar_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W, int C,
                      int KH, int KW, int stride, int pad, int Ho, int Wo, int kp) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long rows = static_cast<long long>(N) * Ho * Wo;
   const long long total = rows * kp;
   const int K = KH * KW * C;
@@ -72,6 +77,8 @@ im2col_scalar_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
 __global__ void __launch_bounds__(CV_THREADS)
 col2im_vec_kernel(const uint4* __restrict__ col, uint4* __restrict__ dx, int N, int H, int W, int C8, int KH, int KW,
                   int stride, int pad, int Ho, int Wo, int kp8) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long total = static_cast<long long>(N) * H * W * C8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -108,6 +115,8 @@ col2im_vec_kernel(const uint4* __restrict__ col, uint4* __restrict__ dx, int N, 
 __global__ void __launch_bounds__(CV_THREADS)
 maxpool_kernel(const __nv_bfloat162* __restrict__ x, __nv_bfloat162* __restrict__ y, int2* __restrict__ arg, int N,
                int H, int W, int C2, int k, int stride, int pad, int Ho, int Wo) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long total = static_cast<long long>(N) * Ho * Wo * C2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -139,6 +148,8 @@ __global__ void __launch_bounds__(CV_THREADS)
 maxpool_bwd_gather_kernel(const __nv_bfloat162* __restrict__ dy, const int2* __restrict__ arg,
                           __nv_bfloat162* __restrict__ dx, int N, int H, int W, int C2, int Ho, int Wo, int k,
                           int stride, int pad) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long total = static_cast<long long>(N) * H * W * C2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -174,6 +185,8 @@ maxpool_bwd_gather_kernel(const __nv_bfloat162* __restrict__ dy, const int2* __r
 // global average pool [N, HW, C] -> [N, C] and its backward
 __global__ void __launch_bounds__(CV_THREADS)
 avgpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int HW, int C) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long total = static_cast<long long>(N) * C;
   const float inv = 1.f / HW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -187,6 +200,8 @@ avgpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ 
 }
 __global__ void __launch_bounds__(CV_THREADS)
 avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int N, int HW, int C) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long total = static_cast<long long>(N) * HW * C;
   const float inv = 1.f / HW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -207,11 +222,11 @@ extern "C" int b200_im2col_nhwc(const void* x, void* col, int N, int H, int W, i
   const long long rows = static_cast<long long>(N) * Ho * Wo;
   if (rows <= 0) return 0;
   if (C % 8 == 0 && kp % 8 == 0) {
-    im2col_vec_kernel<<<cv_grid(rows * (kp / 8)), CV_THREADS, 0, stream>>>(
+    launch_pdl(im2col_vec_kernel, cv_grid(rows * (kp / 8)), CV_THREADS, 0, stream, 
         reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(col), N, H, W, C / 8, KH, KW, stride, pad, Ho, Wo,
         kp / 8);
   } else {
-    im2col_scalar_kernel<<<cv_grid(rows * kp), CV_THREADS, 0, stream>>>(
+    launch_pdl(im2col_scalar_kernel, cv_grid(rows * kp), CV_THREADS, 0, stream, 
         reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(col), N, H, W, C, KH, KW, stride,
         pad, Ho, Wo, kp);
   }
@@ -222,7 +237,7 @@ extern "C" int b200_col2im_nhwc(const void* col, void* dx, int N, int H, int W, 
   if (C % 8 || kp % 8) return -2;
   const long long total = static_cast<long long>(N) * H * W * (C / 8);
   if (total <= 0) return 0;
-  col2im_vec_kernel<<<cv_grid(total), CV_THREADS, 0, stream>>>(reinterpret_cast<const uint4*>(col),
+  launch_pdl(col2im_vec_kernel, cv_grid(total), CV_THREADS, 0, stream, reinterpret_cast<const uint4*>(col),
                                                                reinterpret_cast<uint4*>(dx), N, H, W, C / 8, KH, KW,
                                                                stride, pad, Ho, Wo, kp / 8);
   RET_LAST();
@@ -232,7 +247,7 @@ extern "C" int b200_maxpool_nhwc(const void* x, void* y, int* argmax, int N, int
   if (C % 2) return -2;
   const long long total = static_cast<long long>(N) * Ho * Wo * (C / 2);
   if (total <= 0) return 0;
-  maxpool_kernel<<<cv_grid(total), CV_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat162*>(x),
+  launch_pdl(maxpool_kernel, cv_grid(total), CV_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat162*>(x),
                                                             reinterpret_cast<__nv_bfloat162*>(y),
                                                             reinterpret_cast<int2*>(argmax), N, H, W, C / 2, k, stride,
                                                             pad, Ho, Wo);
@@ -243,7 +258,7 @@ extern "C" int b200_maxpool_bwd_nhwc(const void* dy, const int* argmax, void* dx
   if (C % 2) return -2;
   const long long total = static_cast<long long>(N) * H * W * (C / 2);
   if (total <= 0) return 0;
-  maxpool_bwd_gather_kernel<<<cv_grid(total), CV_THREADS, 0, stream>>>(
+  launch_pdl(maxpool_bwd_gather_kernel, cv_grid(total), CV_THREADS, 0, stream, 
       reinterpret_cast<const __nv_bfloat162*>(dy), reinterpret_cast<const int2*>(argmax),
       reinterpret_cast<__nv_bfloat162*>(dx), N, H, W, C / 2, Ho, Wo, k, stride, pad);
   RET_LAST();
@@ -251,14 +266,14 @@ extern "C" int b200_maxpool_bwd_nhwc(const void* dy, const int* argmax, void* dx
 extern "C" int b200_avgpool_nhwc(const void* x, void* y, int N, int HW, int C, cudaStream_t stream) {
   const long long total = static_cast<long long>(N) * C;
   if (total <= 0) return 0;
-  avgpool_kernel<<<cv_grid(total), CV_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  launch_pdl(avgpool_kernel, cv_grid(total), CV_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x),
                                                             reinterpret_cast<__nv_bfloat16*>(y), N, HW, C);
   RET_LAST();
 }
 extern "C" int b200_avgpool_bwd_nhwc(const void* dy, void* dx, int N, int HW, int C, cudaStream_t stream) {
   const long long total = static_cast<long long>(N) * HW * C;
   if (total <= 0) return 0;
-  avgpool_bwd_kernel<<<cv_grid(total), CV_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(dy),
+  launch_pdl(avgpool_bwd_kernel, cv_grid(total), CV_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(dy),
                                                                 reinterpret_cast<__nv_bfloat16*>(dx), N, HW, C);
   RET_LAST();
 }

@@ -3,6 +3,7 @@
 // (bias gradients), ReLU / GELU pieces.  All use 16-byte vectors and grid-stride loops sized to
 // 148 SMs x a few resident CTAs.
 #include "launch.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -23,6 +24,8 @@ __global__ void __launch_bounds__(EW_THREADS)
 fused_sgd_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ mom,
                  __nv_bfloat16* __restrict__ wb, long long n, const float* __restrict__ hyper, int zero_grad,
                  int nesterov) {
+  griddep_launch_dependents();
+  griddep_wait();
   const float lr = hyper[0], mu = hyper[1], wd = hyper[2], damp = hyper[3];
   const long long nv = n >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
@@ -77,6 +80,8 @@ struct WsumArgs {
 };
 template <bool BF16>
 __global__ void __launch_bounds__(EW_THREADS) weighted_sum_kernel(void* __restrict__ dst, WsumArgs a, long long n) {
+  griddep_launch_dependents();
+  griddep_wait();
   constexpr int VEC = BF16 ? 8 : 4;
   const long long nv = n / VEC;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
@@ -126,6 +131,8 @@ __global__ void __launch_bounds__(EW_THREADS) weighted_sum_kernel(void* __restri
 // ------------------------------------------------------------------ casts
 __global__ void __launch_bounds__(EW_THREADS) cast_f32_bf16_kernel(const float* __restrict__ s,
                                                                     __nv_bfloat16* __restrict__ d, long long n) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long nv = n >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -137,6 +144,8 @@ __global__ void __launch_bounds__(EW_THREADS) cast_f32_bf16_kernel(const float* 
 }
 __global__ void __launch_bounds__(EW_THREADS) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s,
                                                                     float* __restrict__ d, long long n) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long nv = n >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -152,6 +161,8 @@ __global__ void __launch_bounds__(EW_THREADS) cast_bf16_f32_kernel(const __nv_bf
 __global__ void __launch_bounds__(EW_THREADS)
 gather_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ idx, uint4* __restrict__ dst,
                    long long n_rows, int row_vecs) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long total = n_rows * row_vecs;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -162,6 +173,8 @@ gather_rows_kernel(const uint4* __restrict__ src, const long long* __restrict__ 
 }
 __global__ void gather_i64_kernel(const long long* __restrict__ src, const long long* __restrict__ idx,
                                   long long* __restrict__ dst, long long n) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     dst[i] = src[idx[i]];
@@ -172,6 +185,8 @@ __global__ void gather_i64_kernel(const long long* __restrict__ src, const long 
 // grid.y over row chunks; partial sums are combined with fp32 atomics.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long rows, int cols) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float s[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -192,6 +207,8 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
 // ------------------------------------------------------------------ small bf16 elementwise ops
 __global__ void __launch_bounds__(EW_THREADS)
 add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, long long nv, int relu) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 x = a[i], y = b[i];
@@ -210,6 +227,8 @@ add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4*
 // dx = dy * (y > 0)
 __global__ void __launch_bounds__(EW_THREADS)
 relu_bwd_kernel(const uint4* __restrict__ y, const uint4* __restrict__ dy, uint4* __restrict__ dx, long long nv) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 a = y[i], b = dy[i];
@@ -235,6 +254,8 @@ __device__ __forceinline__ float gelu_grad_f(float v) {
 }
 __global__ void __launch_bounds__(EW_THREADS)
 gelu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     y[i] = __float2bfloat16_rn(gelu_f(__bfloat162float(x[i])));
@@ -242,6 +263,8 @@ gelu_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, 
 __global__ void __launch_bounds__(EW_THREADS)
 gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                 __nv_bfloat16* __restrict__ dx, long long n) {
+  griddep_launch_dependents();
+  griddep_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * gelu_grad_f(__bfloat162float(x[i])));
@@ -249,6 +272,8 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 // dst[r, 0:kp] = src[r, 0:k] zero padded (weights whose K is not a multiple of 8, e.g. 7x7x3 = 147)
 __global__ void __launch_bounds__(EW_THREADS)
 pad_rows_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ d, long long rows, int k, int kp) {
+  griddep_launch_dependents();
+  griddep_wait();
   const long long total = rows * kp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -266,7 +291,7 @@ using namespace b200;
 extern "C" int b200_fused_sgd(float* w, float* g, float* mom, void* w_bf16, long long n, const float* hyper,
                               int zero_grad, int nesterov, cudaStream_t stream) {
   if (n <= 0) return 0;
-  fused_sgd_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, stream>>>(w, g, mom, reinterpret_cast<__nv_bfloat16*>(w_bf16), n,
+  launch_pdl(fused_sgd_kernel, ew_grid(n >> 2), EW_THREADS, 0, stream, w, g, mom, reinterpret_cast<__nv_bfloat16*>(w_bf16), n,
                                                                 hyper, zero_grad, nesterov);
   RET_LAST();
 }
@@ -278,19 +303,19 @@ extern "C" int b200_weighted_sum(void* dst, const void* const* srcs, const float
   a.n_src = n_src;
   for (int k = 0; k < n_src; ++k) { a.src[k] = srcs[k]; a.w[k] = weights[k]; }
   if (dtype == 1)
-    weighted_sum_kernel<true><<<ew_grid(n / 8), EW_THREADS, 0, stream>>>(dst, a, n);
+    launch_pdl(weighted_sum_kernel<true>, ew_grid(n / 8), EW_THREADS, 0, stream, dst, a, n);
   else
-    weighted_sum_kernel<false><<<ew_grid(n / 4), EW_THREADS, 0, stream>>>(dst, a, n);
+    launch_pdl(weighted_sum_kernel<false>, ew_grid(n / 4), EW_THREADS, 0, stream, dst, a, n);
   RET_LAST();
 }
 extern "C" int b200_cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
-  cast_f32_bf16_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  launch_pdl(cast_f32_bf16_kernel, ew_grid(n >> 2), EW_THREADS, 0, stream, src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   RET_LAST();
 }
 extern "C" int b200_cast_bf16_f32(const void* src, float* dst, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
-  cast_bf16_f32_kernel<<<ew_grid(n >> 2), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+  launch_pdl(cast_bf16_f32_kernel, ew_grid(n >> 2), EW_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
   RET_LAST();
 }
 extern "C" int b200_gather_rows(const void* src, const long long* idx, void* dst, long long n_rows,
@@ -298,14 +323,14 @@ extern "C" int b200_gather_rows(const void* src, const long long* idx, void* dst
   if (n_rows <= 0) return 0;
   if (row_bytes % 16) return -2;
   const int rv = static_cast<int>(row_bytes / 16);
-  gather_rows_kernel<<<ew_grid(n_rows * rv), EW_THREADS, 0, stream>>>(reinterpret_cast<const uint4*>(src), idx,
+  launch_pdl(gather_rows_kernel, ew_grid(n_rows * rv), EW_THREADS, 0, stream, reinterpret_cast<const uint4*>(src), idx,
                                                                       reinterpret_cast<uint4*>(dst), n_rows, rv);
   RET_LAST();
 }
 extern "C" int b200_gather_rows_i64(const long long* src, const long long* idx, long long* dst, long long n,
                                     cudaStream_t stream) {
   if (n <= 0) return 0;
-  gather_i64_kernel<<<ew_grid(n, 64), EW_THREADS, 0, stream>>>(src, idx, dst, n);
+  launch_pdl(gather_i64_kernel, ew_grid(n, 64), EW_THREADS, 0, stream, src, idx, dst, n);
   RET_LAST();
 }
 extern "C" int b200_colsum(const void* x, float* out, long long rows, int cols, int accumulate, cudaStream_t stream) {
@@ -314,13 +339,13 @@ extern "C" int b200_colsum(const void* x, float* out, long long rows, int cols, 
   long long gy = (rows + 63) / 64;
   if (gy > 64) gy = 64;
   dim3 grid((cols + 31) / 32, static_cast<unsigned>(gy));
-  colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols);
+  launch_pdl(colsum_kernel, grid, 256, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), out, rows, cols);
   RET_LAST();
 }
 extern "C" int b200_add_bf16(const void* a, const void* b, void* out, long long n, int relu, cudaStream_t stream) {
   if (n <= 0) return 0;
   if (n % 8) return -2;
-  add_bf16_kernel<<<ew_grid(n / 8), EW_THREADS, 0, stream>>>(reinterpret_cast<const uint4*>(a),
+  launch_pdl(add_bf16_kernel, ew_grid(n / 8), EW_THREADS, 0, stream, reinterpret_cast<const uint4*>(a),
                                                              reinterpret_cast<const uint4*>(b),
                                                              reinterpret_cast<uint4*>(out), n / 8, relu);
   RET_LAST();
@@ -328,27 +353,27 @@ extern "C" int b200_add_bf16(const void* a, const void* b, void* out, long long 
 extern "C" int b200_relu_bwd_bf16(const void* y, const void* dy, void* dx, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
   if (n % 8) return -2;
-  relu_bwd_kernel<<<ew_grid(n / 8), EW_THREADS, 0, stream>>>(reinterpret_cast<const uint4*>(y),
+  launch_pdl(relu_bwd_kernel, ew_grid(n / 8), EW_THREADS, 0, stream, reinterpret_cast<const uint4*>(y),
                                                              reinterpret_cast<const uint4*>(dy),
                                                              reinterpret_cast<uint4*>(dx), n / 8);
   RET_LAST();
 }
 extern "C" int b200_gelu_bf16(const void* x, void* y, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
-  gelu_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  launch_pdl(gelu_kernel, ew_grid(n), EW_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x),
                                                      reinterpret_cast<__nv_bfloat16*>(y), n);
   RET_LAST();
 }
 extern "C" int b200_gelu_bwd_bf16(const void* x, const void* dy, void* dx, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
-  gelu_bwd_kernel<<<ew_grid(n), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+  launch_pdl(gelu_bwd_kernel, ew_grid(n), EW_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x),
                                                          reinterpret_cast<const __nv_bfloat16*>(dy),
                                                          reinterpret_cast<__nv_bfloat16*>(dx), n);
   RET_LAST();
 }
 extern "C" int b200_pad_rows_bf16(const void* src, void* dst, long long rows, int k, int kp, cudaStream_t stream) {
   if (rows <= 0) return 0;
-  pad_rows_kernel<<<ew_grid(rows * kp), EW_THREADS, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(src),
+  launch_pdl(pad_rows_kernel, ew_grid(rows * kp), EW_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(src),
                                                                  reinterpret_cast<__nv_bfloat16*>(dst), rows, k, kp);
   RET_LAST();
 }

@@ -2,6 +2,7 @@
 // bytes, e.g. the 10-class classifier head) -- tiny problems only.  Same contract as
 // b200_gemm_bf16: D = act(alpha * A B^T + bias) with K-major or MN-major bf16 operands.
 #include "launch.h"
+#include "pdl.cuh"
 #include <cuda_bf16.h>
 
 namespace b200 {
@@ -20,6 +21,8 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B, void* __restrict__ D,
                  const float* __restrict__ bias, int M, int N, int K, long long lda, long long ldb, long long ldd,
                  int a_mn, int b_mn, int out_fp32, int act, int accumulate, float alpha) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float sa[32][33];
   __shared__ float sb[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -81,7 +84,7 @@ extern "C" int b200_gemm_simt(const void* a, const void* b, void* d, const float
                               int accumulate, float alpha, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return 0;
   dim3 grid((N + 31) / 32, (M + 31) / 32);
-  b200::gemm_simt_kernel<<<grid, 256, 0, stream>>>(
+  b200::launch_pdl(b200::gemm_simt_kernel, grid, 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), d, bias, M, N, K, lda,
       ldb, ldd, a_mn, b_mn, out_fp32, act, accumulate, alpha);
   return static_cast<int>(cudaGetLastError());

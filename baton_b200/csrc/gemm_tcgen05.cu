@@ -19,6 +19,7 @@
 // as they land over NVLink.
 #include "ptx.cuh"
 #include "launch.h"
+#include "pdl.cuh"
 
 namespace b200 {
 
@@ -76,6 +77,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+  griddep_launch_dependents();  // PDL: the next kernel may start its prologue now
   const int warp = threadIdx.x >> 5;
   const int m0 = blockIdx.y * BM;
   const int n0 = blockIdx.x * BN;
@@ -105,6 +107,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // PDL: everything above overlapped the previous kernel; its results are visible from here
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -293,7 +296,8 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  gemm_bf16_tcgen05_kernel<BN, STAGES><<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+  cudaError_t le = launch_pdl(gemm_bf16_tcgen05_kernel<BN, STAGES>, grid, GEMM_THREADS, smem, stream, ta, tb, p);
+  if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
 

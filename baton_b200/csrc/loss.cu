@@ -2,6 +2,7 @@
 // into a device scalar that the trainer reads ONCE per epoch (the reference does float(loss) -- a
 // host sync -- on every batch: utils.py:88).
 #include "launch.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -31,6 +32,8 @@ template <bool IN_FP32, bool OUT_FP32>
 __global__ void __launch_bounds__(256)
 softmax_xent_kernel(const void* __restrict__ logits, const long long* __restrict__ target, void* __restrict__ dlogits,
                     float* __restrict__ loss_acc, long long rows, int C, long long ld, float grad_scale) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   float my_loss = 0.f, my_hit = 0.f;
@@ -87,6 +90,8 @@ template <bool IN_FP32, bool OUT_FP32>
 __global__ void __launch_bounds__(256)
 mse_kernel(const void* __restrict__ pred, const float* __restrict__ target, void* __restrict__ dpred,
            float* __restrict__ loss_acc, long long n, float grad_scale) {
+  griddep_launch_dependents();
+  griddep_wait();
   float acc = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -120,7 +125,7 @@ extern "C" int b200_softmax_xent(const void* logits, int logits_fp32, const long
                                  cudaStream_t stream) {
   if (rows <= 0) return 0;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-#define XENT(A, B) softmax_xent_kernel<A, B><<<grid, 256, 0, stream>>>(logits, target, dlogits, loss_acc, rows, C, ld, grad_scale)
+#define XENT(A, B) launch_pdl(softmax_xent_kernel<A, B>, grid, 256, 0, stream, logits, target, dlogits, loss_acc, rows, C, ld, grad_scale)
   if (logits_fp32) { if (dl_fp32) XENT(true, true); else XENT(true, false); }
   else             { if (dl_fp32) XENT(false, true); else XENT(false, false); }
 #undef XENT
@@ -133,7 +138,7 @@ extern "C" int b200_mse(const void* pred, int pred_fp32, const float* target, vo
   long long g = (n + 255) / 256;
   if (g > 148 * 4) g = 148 * 4;
   const unsigned grid = static_cast<unsigned>(g);
-#define MSE(A, B) mse_kernel<A, B><<<grid, 256, 0, stream>>>(pred, target, dpred, loss_acc, n, grad_scale)
+#define MSE(A, B) launch_pdl(mse_kernel<A, B>, grid, 256, 0, stream, pred, target, dpred, loss_acc, n, grad_scale)
   if (pred_fp32) { if (dp_fp32) MSE(true, true); else MSE(true, false); }
   else           { if (dp_fp32) MSE(false, true); else MSE(false, false); }
 #undef MSE

@@ -2,6 +2,7 @@
 // [rows, C] bf16 matrix (fused residual add + ReLU, running-stat update), LayerNorm forward /
 // backward (fused residual add) and row softmax for attention.  Statistics and gradients in fp32.
 #include "launch.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -10,6 +11,8 @@ namespace b200 {
 // sums[0:C] += sum_r x[r,c] ; sums[C:2C] += sum_r x[r,c]^2.  Block = 32 channel pairs x 8 row lanes.
 __global__ void __launch_bounds__(256)
 bn_stats_kernel(const __nv_bfloat162* __restrict__ x, float* __restrict__ sums, long long rows, int C) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float s[4][8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int C2 = C >> 1;
@@ -41,6 +44,8 @@ bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, uint
                 float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ save_mean,
                 float* __restrict__ save_rstd, long long* __restrict__ nbt, long long rows, int C, float eps,
                 float momentum, int relu, int training) {
+  griddep_launch_dependents();
+  griddep_wait();
   extern __shared__ float sm[];  // scale[C], shift[C]
   if (training && nbt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;  // num_batches_tracked
   float* scale = sm;
@@ -101,6 +106,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const __nv_bfloat162* __restrict__ x, const __nv_bfloat162* __restrict__ y,
                      const __nv_bfloat162* __restrict__ dy, const float* __restrict__ mean,
                      const float* __restrict__ rstd, float* __restrict__ sums, long long rows, int C, int relu) {
+  griddep_launch_dependents();
+  griddep_wait();
   __shared__ float s[4][8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int C2 = C >> 1;
@@ -139,6 +146,8 @@ bn_bwd_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, co
                     uint4* __restrict__ dx, uint4* __restrict__ dres, const float* __restrict__ gamma,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ sums,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C, int relu) {
+  griddep_launch_dependents();
+  griddep_wait();
   extern __shared__ float sm[];  // a[C], b[C], m[C], r[C]
   float* ka = sm;
   float* kb = sm + C;
@@ -213,6 +222,8 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                      __nv_bfloat16* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
                      float* __restrict__ mean, float* __restrict__ rstd, long long rows, int C, float eps) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -250,6 +261,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
                      __nv_bfloat16* __restrict__ dx, const float* __restrict__ gamma, const float* __restrict__ mean,
                      const float* __restrict__ rstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      long long rows, int C) {
+  griddep_launch_dependents();
+  griddep_wait();
   extern __shared__ float sm[];  // dgamma[C], dbeta[C] partials of this block
   float* sg = sm;
   float* sb = sm + C;
@@ -291,6 +304,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows, int C,
                    float scale) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -317,6 +332,8 @@ softmax_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
                    __nv_bfloat16* __restrict__ dx, long long rows, int C, float scale) {
+  griddep_launch_dependents();
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -357,7 +374,7 @@ using namespace b200;
 extern "C" int b200_bn_stats(const void* x, float* sums, long long rows, int C, cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (C % 2) return -2;
-  bn_stats_kernel<<<colred_grid(rows, C), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat162*>(x), sums, rows, C);
+  launch_pdl(bn_stats_kernel, colred_grid(rows, C), 256, 0, stream, reinterpret_cast<const __nv_bfloat162*>(x), sums, rows, C);
   RET_LAST();
 }
 extern "C" int b200_bn_apply(const void* x, const void* residual, void* y, float* sums, const float* gamma,
@@ -366,7 +383,7 @@ extern "C" int b200_bn_apply(const void* x, const void* residual, void* y, float
                              int relu, int training, cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (C % 8) return -2;
-  bn_apply_kernel<<<stream_grid(rows * (C / 8)), 256, 2 * C * sizeof(float), stream>>>(
+  launch_pdl(bn_apply_kernel, stream_grid(rows * (C / 8)), 256, 2 * C * sizeof(float), stream, 
       reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(residual), reinterpret_cast<uint4*>(y), sums,
       gamma, beta, running_mean, running_var, save_mean, save_rstd, nbt, rows, C, eps, momentum, relu, training);
   RET_LAST();
@@ -376,7 +393,7 @@ extern "C" int b200_bn_bwd_reduce(const void* x, const void* y, const void* dy, 
                                   cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (C % 2) return -2;
-  bn_bwd_reduce_kernel<<<colred_grid(rows, C), 256, 0, stream>>>(
+  launch_pdl(bn_bwd_reduce_kernel, colred_grid(rows, C), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat162*>(x), reinterpret_cast<const __nv_bfloat162*>(y),
       reinterpret_cast<const __nv_bfloat162*>(dy), save_mean, save_rstd, sums, rows, C, relu);
   RET_LAST();
@@ -386,7 +403,7 @@ extern "C" int b200_bn_bwd_apply(const void* x, const void* y, const void* dy, v
                                  float* dbeta, long long rows, int C, int relu, cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (C % 8) return -2;
-  bn_bwd_apply_kernel<<<stream_grid(rows * (C / 8)), 256, 4 * C * sizeof(float), stream>>>(
+  launch_pdl(bn_bwd_apply_kernel, stream_grid(rows * (C / 8)), 256, 4 * C * sizeof(float), stream, 
       reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(y), reinterpret_cast<const uint4*>(dy),
       reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dres), gamma, save_mean, save_rstd, sums, dgamma, dbeta,
       rows, C, relu);
@@ -397,7 +414,7 @@ extern "C" int b200_layernorm_fwd(const void* x, const void* residual, void* y, 
   if (rows <= 0) return 0;
   if (C > 32 * LN_MAX_PER_LANE) return -2;
   const int warps = 8;
-  layernorm_fwd_kernel<<<static_cast<unsigned>((rows + warps - 1) / warps), warps * 32, 0, stream>>>(
+  launch_pdl(layernorm_fwd_kernel, static_cast<unsigned>((rows + warps - 1) / warps), warps * 32, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(residual),
       reinterpret_cast<__nv_bfloat16*>(y), gamma, beta, mean, rstd, rows, C, eps);
   RET_LAST();
@@ -409,7 +426,7 @@ extern "C" int b200_layernorm_bwd(const void* x, const void* dy, void* dx, const
   if (C > 32 * LN_MAX_PER_LANE) return -2;
   long long g = (rows + 7) / 8;
   if (g > 148 * 2) g = 148 * 2;
-  layernorm_bwd_kernel<<<static_cast<unsigned>(g), 256, 2 * C * sizeof(float), stream>>>(
+  launch_pdl(layernorm_bwd_kernel, static_cast<unsigned>(g), 256, 2 * C * sizeof(float), stream, 
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy),
       reinterpret_cast<__nv_bfloat16*>(dx), gamma, mean, rstd, dgamma, dbeta, rows, C);
   RET_LAST();
@@ -417,7 +434,7 @@ extern "C" int b200_layernorm_bwd(const void* x, const void* dy, void* dx, const
 extern "C" int b200_softmax_fwd(const void* x, void* y, long long rows, int C, float scale, cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (C > 32 * LN_MAX_PER_LANE) return -2;
-  softmax_fwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+  launch_pdl(softmax_fwd_kernel, static_cast<unsigned>((rows + 7) / 8), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), rows, C, scale);
   RET_LAST();
 }
@@ -425,7 +442,7 @@ extern "C" int b200_softmax_bwd(const void* y, const void* dy, void* dx, long lo
                                 cudaStream_t stream) {
   if (rows <= 0) return 0;
   if (C > 32 * LN_MAX_PER_LANE) return -2;
-  softmax_bwd_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, stream>>>(
+  launch_pdl(softmax_bwd_kernel, static_cast<unsigned>((rows + 7) / 8), 256, 0, stream, 
       reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dy),
       reinterpret_cast<__nv_bfloat16*>(dx), rows, C, scale);
   RET_LAST();
