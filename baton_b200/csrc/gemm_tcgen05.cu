@@ -1,22 +1,31 @@
 // bf16 GEMM on the 5th-gen tensor cores: TMA -> 128B-swizzled smem ring -> tcgen05.mma
 // (accumulator in TMEM) -> tcgen05.ld epilogue with fused bias / activation / cast.
 //
-//     D[M,N] = act( A[M,K] * B[N,K]^T + bias[N] )          (A, B bf16; accumulate fp32)
+//     D[M,N] = act( alpha * A[M,K] * B[N,K]^T + bias[N] )          (A, B bf16; accumulate fp32)
 //
 // Each operand may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]), so the
 // three training GEMMs need no transposes:
 //     fwd    Y  = X  W^T      A = X   (K-major)   B = W  (K-major)
-//     dgrad  dX = dY W        A = dY  (K-major)   B = W  (MN-major, W stored [N_out... K_red] rows)
+//     dgrad  dX = dY W        A = dY  (K-major)   B = W  (MN-major)
 //     wgrad  dW = dY^T X      A = dY  (MN-major)  B = X  (MN-major)
 //
-// Warp roles (256 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one elected
-// lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (warp q reads TMEM lanes 32q..32q+31).
-// Split-K (gridDim.z) accumulates with fp32 red.global.add into a zero-initialised D.
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (warp q reads TMEM lanes 32q..32q+31).
+// The pipeline depth is a runtime value sized to the K extent, so short-K GEMMs ask for little
+// shared memory and several CTAs share an SM (one CTA's epilogue overlaps another's main loop).
 //
-// Flag-gated variant ("bcast_gemm", K3 in SURVEY.md 2.6): the producer acquires a per-N-tile
-// arrival flag (written by the broadcast kernel with st.release.sys) before issuing the TMA
-// loads of a B tile, so the first GEMM of a round consumes the new global weights tile by tile
-// as they land over NVLink.
+// Split-K, two flavours:
+//   * atomic   (fp32 output, gradient accumulation): gridDim.z slices red.global.add into D;
+//   * cluster  (any output): the z-slices of one output tile form a thread-block CLUSTER; each CTA
+//     parks its fp32 partial tile in its own shared memory, and after a cluster barrier CTA r
+//     reduces rows [r*128/S, (r+1)*128/S) of all S partials through distributed shared memory
+//     (ld.shared::cluster), applies the epilogue and stores -- no workspace, no second kernel.
+//     This is what makes the deep layers of a ResNet (M = 128, K = 4608) use more than 8 SMs.
+//
+// Flag-gated variant ("bcast_gemm", K3 in SURVEY.md 2.6): the producer acquires per-arena-tile
+// arrival flags (published by the FedAvg kernel with st.release) before issuing the TMA loads of
+// a weight tile, so the first GEMM of a round consumes the new global weights tile by tile while
+// the rest of the model is still landing over NVLink.
 #include "ptx.cuh"
 #include "launch.h"
 #include "pdl.cuh"
@@ -27,6 +36,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 256;
+constexpr int MAX_STAGES = 8;
 
 struct GemmParams {
   int M, N, K;
@@ -37,7 +47,9 @@ struct GemmParams {
   int act;                // 0 none, 1 relu, 2 gelu(tanh)
   int a_mn, b_mn;         // operand majors
   int k_tiles_per_split;  // split-K: k tiles handled by one z-slice
-  int atomic_out;         // 1: red.add fp32 into D (split-K)
+  int atomic_out;         // 1: red.add fp32 into D
+  int cluster_k;          // > 1: z-slices form a cluster of this size and reduce through DSMEM
+  int stages;             // pipeline depth (1..MAX_STAGES)
   const uint32_t* tile_flags;  // optional arrival flags, one per arena tile (bcast_gemm)
   uint32_t flag_epoch;         // value a flag must reach before the data under it may be loaded
   long long flag_elem_off;     // arena element offset of B[0,0]
@@ -52,6 +64,8 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int PART_PITCH = BN + 4;                  // floats; +4 keeps float4 alignment, skews banks
+  static constexpr int PART_BYTES = BM * PART_PITCH * 4;     // fp32 partial tile for the cluster reduce
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -64,7 +78,73 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-template <int BN, int STAGES>
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(remote)
+               : "memory");
+  return v;
+}
+
+// bias + activation + cast + store of `NV` consecutive output columns of one row
+template <int NV>
+__device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, int col0, float (&v)[NV], bool vec_ok) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float x = v[j] * p.alpha;
+    if (p.bias != nullptr && (col0 + j) < p.N) x += p.bias[col0 + j];
+    v[j] = apply_act(x, p.act);
+  }
+  const bool full = (col0 + NV <= p.N);
+  if (p.out_fp32) {
+    float* d = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+    if (p.atomic_out) {
+      if (full && vec_ok) {
+#pragma unroll
+        for (int j = 0; j < NV; j += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(v[j]), "f"(v[j + 1]),
+                       "f"(v[j + 2]), "f"(v[j + 3])
+                       : "memory");
+      } else {
+        for (int j = 0; j < NV && col0 + j < p.N; ++j) atomicAdd(d + j, v[j]);
+      }
+    } else if (full && vec_ok) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      for (int j = 0; j < NV && col0 + j < p.N; ++j) d[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+    if (full && vec_ok) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(v[j], v[j + 1]);
+        o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+        o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+        o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(d + j) = o;
+      }
+    } else {
+      for (int j = 0; j < NV && col0 + j < p.N; ++j) d[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
@@ -72,9 +152,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16B aligned: realign to the 1024B the 128B swizzle needs
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  const int STAGES = p.stages;
+  const int ring_bytes = STAGES * L::STAGE_BYTES;
+  const int data_bytes = (p.cluster_k > 1 && L::PART_BYTES > ring_bytes) ? L::PART_BYTES : ring_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + data_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   griddep_launch_dependents();  // PDL: the next kernel may start its prologue now
@@ -131,9 +214,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         fence_proxy_async_all();  // order the acquires before the async-proxy (TMA) reads of global memory
       }
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < num_kt; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + s * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
@@ -152,14 +235,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0);
         }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    int s = 0;
+    uint32_t ph = 0;
     for (int i = 0; i < num_kt; ++i) {
-      const int s = i % STAGES;
-      const uint32_t ph = (i / STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (elect_one()) {
@@ -180,69 +264,66 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (i == num_kt - 1) tc_commit(tmem_full_bar);  // accumulator complete
       }
       __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1; }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (phase 1) =====================
     const int q = warp & 3;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int row = m0 + q * 32 + static_cast<int>(lane_id());
-    const bool row_ok = row < p.M;
+    const int lrow = q * 32 + static_cast<int>(lane_id());
+    const int row = m0 + lrow;
     const size_t elt = p.out_fp32 ? 4 : 2;
-    uint8_t* drow = reinterpret_cast<uint8_t*>(p.D) + static_cast<size_t>(row) * p.ldd * elt;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * elt) % 16 == 0);
+    float* part = reinterpret_cast<float*>(smem);  // cluster mode: reuse the (drained) operand ring
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       tmem_ld_wait();
-      const int col0 = n0 + c;
-      if (!row_ok || col0 >= p.N) continue;
-      float v[32];
+      if (p.cluster_k > 1) {
+        float4* dst = reinterpret_cast<float4*>(part + lrow * L::PART_PITCH + c);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias != nullptr && (col0 + j) < p.N) x += p.bias[col0 + j];
-        v[j] = apply_act(x, p.act);
-      }
-      const bool full = (col0 + 32 <= p.N);
-      if (p.atomic_out) {
-        float* d = reinterpret_cast<float*>(drow) + col0;
-        if (full && vec_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(v[j]), "f"(v[j + 1]),
-                         "f"(v[j + 2]), "f"(v[j + 3])
-                         : "memory");
-        } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) atomicAdd(d + j, v[j]);
-        }
-      } else if (p.out_fp32) {
-        float* d = reinterpret_cast<float*>(drow) + col0;
-        if (full && vec_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) d[j] = v[j];
-        }
+        for (int j = 0; j < 32; j += 4)
+          dst[j >> 2] = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                    __uint_as_float(r[j + 3]));
       } else {
-        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(drow) + col0;
-        if (full && vec_ok) {
+        const int col0 = n0 + c;
+        if (row >= p.M || col0 >= p.N) continue;
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(v[j], v[j + 1]);
-            o.y = pack_bf16x2(v[j + 2], v[j + 3]);
-            o.z = pack_bf16x2(v[j + 4], v[j + 5]);
-            o.w = pack_bf16x2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(d + j) = o;
-          }
-        } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) d[j] = __float2bfloat16_rn(v[j]);
-        }
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        store_row_chunk<32>(p, row, col0, v, vec_ok);
       }
     }
+  }
+
+  if (p.cluster_k > 1) {
+    // ===================== cluster split-K: reduce the S partial tiles through DSMEM =====================
+    const int S = p.cluster_k;
+    cluster_sync_all();  // every CTA's partial tile is in its shared memory
+    if (warp >= 4) {
+      const uint32_t me = cluster_ctarank();
+      const int rows_per = BM / S;                 // S in {2, 4, 8}
+      constexpr int CG = BN / 8;                   // 8-column groups per row
+      const int t = threadIdx.x - 128;             // 0..127
+      const size_t elt = p.out_fp32 ? 4 : 2;
+      const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * elt) % 16 == 0);
+      for (int item = t; item < rows_per * CG; item += 128) {
+        const int lrow = static_cast<int>(me) * rows_per + item / CG;
+        const int c = (item % CG) * 8;
+        const uint32_t laddr = smem_u32(smem) + static_cast<uint32_t>((lrow * L::PART_PITCH + c) * 4);
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < S; ++r) {              // fixed order: deterministic sum
+          const float4 a = ld_dsmem_f4(laddr, r), b = ld_dsmem_f4(laddr + 16, r);
+          v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+          v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+        }
+        const int row = m0 + lrow, col0 = n0 + c;
+        if (row < p.M && col0 < p.N) store_row_chunk<8>(p, row, col0, v, vec_ok);
+      }
+    }
+    cluster_sync_all();  // nobody leaves (and frees its smem) while a peer may still read it
   }
 
   tc_fence_before();
@@ -285,18 +366,44 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-template <int BN, int STAGES>
+template <int BN>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
                       cudaStream_t stream) {
-  constexpr int smem = STAGES * SmemLayout<BN>::STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  using L = SmemLayout<BN>;
+  constexpr int max_stages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  constexpr int max_smem = max_stages * L::STAGE_BYTES + (2 * MAX_STAGES + 1) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, STAGES>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         max_smem > L::PART_BYTES + 2048 ? max_smem : L::PART_BYTES + 2048);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  cudaError_t le = launch_pdl(gemm_bf16_tcgen05_kernel<BN, STAGES>, grid, GEMM_THREADS, smem, stream, ta, tb, p);
+  int ring = p.stages * L::STAGE_BYTES;
+  if (p.cluster_k > 1 && L::PART_BYTES > ring) ring = L::PART_BYTES;
+  const int smem = ring + (2 * MAX_STAGES + 1) * 8 + 16 + 1024;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (p.cluster_k > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = p.cluster_k;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN>, ta, tb, p);
   if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
@@ -306,13 +413,14 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
 // D = act(alpha * A B^T + bias).  a/b: bf16 device pointers.
 //   a_mn == 0: A is row-major [M, K] with pitch lda;  a_mn == 1: A is row-major [K, M] with pitch lda
 //   b_mn == 0: B is row-major [N, K] with pitch ldb;  b_mn == 1: B is row-major [K, N] with pitch ldb
+//   split_k > 1 with accumulate / fp32 atomic output -> atomic split-K; split_k < 0 -> cluster split-K of
+//   size -split_k (2, 4 or 8) for any output type.
 // Returns 0 on success, a CUDA / driver error code otherwise, -2 on unsupported alignment.
 extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float* bias, int M, int N, int K,
                               long long lda, long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act,
                               int split_k, int accumulate, float alpha, const uint32_t* tile_flags,
-                              uint32_t flag_epoch,
-                              long long flag_elem_off, int flag_tile_elems, long long flag_bias_off, int force_bn,
-                              cudaStream_t stream) {
+                              uint32_t flag_epoch, long long flag_elem_off, int flag_tile_elems,
+                              long long flag_bias_off, int force_bn, cudaStream_t stream) {
   using namespace b200;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
@@ -333,19 +441,30 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
   if (rc) return rc;
 
   const int k_tiles = (K + BK - 1) / BK;
+  int cluster_k = 1;
+  if (split_k < 0) {  // cluster split-K: every z-slice must own at least one k tile
+    cluster_k = -split_k;
+    if (cluster_k != 2 && cluster_k != 4 && cluster_k != 8) return -5;
+    while (cluster_k > 1 && (cluster_k - 1) * ((k_tiles + cluster_k - 1) / cluster_k) >= k_tiles) cluster_k >>= 1;
+    split_k = cluster_k;
+  }
   if (split_k < 1) split_k = 1;
   if (split_k > k_tiles) split_k = k_tiles;
   int per = (k_tiles + split_k - 1) / split_k;
-  split_k = (k_tiles + per - 1) / per;  // no empty z-slices
+  if (cluster_k == 1) split_k = (k_tiles + per - 1) / per;  // no empty z-slices
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.D = d; p.ldd = ldd; p.bias = bias; p.out_fp32 = out_fp32; p.act = act;
-  p.a_mn = a_mn; p.b_mn = b_mn; p.k_tiles_per_split = per; p.atomic_out = (split_k > 1 || accumulate) ? 1 : 0;
+  p.a_mn = a_mn; p.b_mn = b_mn; p.k_tiles_per_split = per;
+  p.cluster_k = cluster_k;
+  p.atomic_out = (accumulate || (split_k > 1 && cluster_k == 1)) ? 1 : 0;
   p.tile_flags = tile_flags; p.flag_epoch = flag_epoch; p.alpha = alpha;
   p.flag_elem_off = flag_elem_off; p.flag_tile_elems = flag_tile_elems; p.ldb = ldb;
   p.flag_bias_off = (tile_flags != nullptr && bias != nullptr) ? flag_bias_off : -1;
   if (p.atomic_out && (!out_fp32 || bias != nullptr || act != 0)) return -3;
+  const int max_stages = (bn == 256) ? 4 : (bn == 128 ? 6 : 8);
+  p.stages = per < max_stages ? (per < 2 ? 2 : per) : max_stages;
   dim3 grid((N + bn - 1) / bn, (M + BM - 1) / BM, split_k);
-  if (bn == 256) return launch_cfg<256, 4>(ta, tb, p, grid, stream);
-  if (bn == 128) return launch_cfg<128, 6>(ta, tb, p, grid, stream);
-  return launch_cfg<64, 8>(ta, tb, p, grid, stream);
+  if (bn == 256) return launch_cfg<256>(ta, tb, p, grid, stream);
+  if (bn == 128) return launch_cfg<128>(ta, tb, p, grid, stream);
+  return launch_cfg<64>(ta, tb, p, grid, stream);
 }

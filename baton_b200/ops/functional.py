@@ -50,6 +50,17 @@ def pick_split_k(M: int, N: int, K: int, bn: int) -> int:
     return max(1, min(k_tiles // 4, NUM_SMS // tiles))
 
 
+def pick_cluster_k(M: int, N: int, K: int, bn: int) -> int:
+    """Cluster split-K factor (1, 2, 4 or 8) for GEMMs with few output tiles and a long K."""
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    k_tiles = (K + 63) // 64
+    best = 1
+    for s in (2, 4, 8):
+        if tiles * s <= NUM_SMS and k_tiles >= 4 * s:
+            best = s
+    return best
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = BF16, bias: Optional[torch.Tensor] = None,
          act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: Optional[int] = None,
@@ -79,7 +90,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         return out
     bn = force_bn or pick_bn(M, N)
     if split_k is None:
-        split_k = pick_split_k(M, N, K, bn) if (accumulate and out.dtype == torch.float32) else 1
+        if accumulate and out.dtype == torch.float32:
+            split_k = pick_split_k(M, N, K, bn)          # atomic split-K straight into the gradient arena
+        else:
+            split_k = -pick_cluster_k(M, N, K, bn)       # cluster split-K, DSMEM reduce (negative = cluster)
+            if split_k == -1:
+                split_k = 1
     if split_k > 1:
         assert out.dtype == torch.float32 and bias is None and act == 0
     C.gemm(a, b, out, bias, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, split_k, accumulate, alpha, flags, flag_epoch,

@@ -87,6 +87,28 @@ def test_gemm_split_k_accumulate_and_pitched_output(F):
     assert _rel(out2, A.float().t() @ Bp[:, :147].float()) < 2e-3
 
 
+@pytest.mark.parametrize("S", [2, 4, 8])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 512, 4608, 64), (512, 256, 2304, 64), (200, 136, 1032, 128), (256, 512, 2048, 256)])
+def test_gemm_cluster_split_k_dsmem_reduce(F, S, M, N, K, bn):
+    """Split-K whose z-slices form a thread-block cluster and reduce through distributed smem."""
+    torch.manual_seed(S + M)
+    dev = _dev()
+    A = torch.randn(M, K, device=dev).to(BF16)
+    B = torch.randn(N, K, device=dev).to(BF16)
+    bias = torch.randn(N, device=dev)
+    ref = torch.relu(A.float() @ B.float().t() + bias)
+    out = F.gemm(A, B, bias=bias, act=1, split_k=-S, force_bn=bn)
+    assert out.dtype == BF16 and _rel(out, ref) < 1e-2, _rel(out, ref)
+    out32 = F.gemm(A, B, bias=bias, act=1, split_k=-S, force_bn=bn, out_dtype=torch.float32)
+    assert _rel(out32, ref) < 2e-3
+    # MN-major operands + accumulate into an existing fp32 buffer
+    acc = torch.ones(M, N, device=dev)
+    F.gemm(A.t().contiguous(), B.t().contiguous(), a_mn=True, b_mn=True, out=acc, accumulate=True, split_k=-S,
+           force_bn=bn) if M % 8 == 0 and N % 8 == 0 else None
+    if M % 8 == 0 and N % 8 == 0:
+        assert _rel(acc, A.float() @ B.float().t() + 1.0) < 2e-3
+
+
 def test_gemm_simt_fallback_small_pitch(F):
     torch.manual_seed(2)
     dev = _dev()
