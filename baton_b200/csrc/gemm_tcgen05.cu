@@ -144,7 +144,196 @@ __device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, in
   }
 }
 
-template <int BN>
+// ---- fixed-depth pipeline, one CTA per SM: the default path ----
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmParams p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16B aligned: realign to the 1024B the 128B swizzle needs
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  griddep_launch_dependents();  // PDL: the next kernel may start its prologue now
+  const int warp = threadIdx.x >> 5;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int k_tiles_total = (p.K + BK - 1) / BK;
+  const int kt_begin = blockIdx.z * p.k_tiles_per_split;
+  int kt_end = kt_begin + p.k_tiles_per_split;
+  if (kt_end > k_tiles_total) kt_end = k_tiles_total;
+  const int num_kt = kt_end - kt_begin;  // host guarantees >= 1 for every launched z
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, BN);  // BN fp32 accumulator columns (power of two >= 32)
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // PDL: everything above overlapped the previous kernel; its results are visible from here
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      if (p.tile_flags != nullptr) {
+        // bcast_gemm: wait until the FedAvg kernel has published every arena tile under the rows
+        // [n0, n0+BN) of the (K-major) weight matrix this CTA is about to TMA-load
+        const int rows_here = (p.N - n0) < BN ? (p.N - n0) : BN;
+        const long long e0 = p.flag_elem_off + static_cast<long long>(n0) * p.ldb;
+        const long long e1 = p.flag_elem_off + static_cast<long long>(n0 + rows_here) * p.ldb - 1;
+        for (long long t = e0 / p.flag_tile_elems; t <= e1 / p.flag_tile_elems; ++t) {
+          while (ld_acquire_sys(p.tile_flags + t) < p.flag_epoch) {
+          }
+        }
+        if (p.flag_bias_off >= 0) {  // the bias slice the epilogue of this CTA will add
+          const long long b0 = p.flag_bias_off + n0, b1 = p.flag_bias_off + n0 + rows_here - 1;
+          for (long long t = b0 / p.flag_tile_elems; t <= b1 / p.flag_tile_elems; ++t) {
+            while (ld_acquire_sys(p.tile_flags + t) < p.flag_epoch) {
+            }
+          }
+        }
+        fence_proxy_async_all();  // order the acquires before the async-proxy (TMA) reads of global memory
+      }
+      for (int i = 0; i < num_kt; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        const int k0 = (kt_begin + i) * BK;
+        mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        if (!p.a_mn) {
+          tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box [64 k][128 rows]
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)  // box [64 m][64 k rows] per MN atom
+            tma_load_2d(sa + j * 8192, &tmA, &full_bar[s], m0 + j * 64, k0);
+        }
+        if (!p.b_mn) {
+          tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box [64 k][BN rows]
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    for (int i = 0; i < num_kt; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // K-major: 8-row groups are 1024 B apart (SBO), K advance = 32 B inside the swizzle row.
+          // MN-major: 64-wide MN atoms are 8192 B apart (LBO), 8-row K groups 1024 B apart (SBO),
+          //           K advance of 16 rows = 2048 B.
+          const uint64_t ad = p.a_mn ? umma_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                     : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+          const uint64_t bd = p.b_mn ? umma_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                     : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+          tc_mma_f16(tmem_base, ad, bd, idesc, (i | k) != 0);
+        }
+        tc_commit(&empty_bar[s]);                       // frees the smem slot when the MMAs retire
+        if (i == num_kt - 1) tc_commit(tmem_full_bar);  // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = m0 + q * 32 + static_cast<int>(lane_id());
+    const bool row_ok = row < p.M;
+    const size_t elt = p.out_fp32 ? 4 : 2;
+    uint8_t* drow = reinterpret_cast<uint8_t*>(p.D) + static_cast<size_t>(row) * p.ldd * elt;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * elt) % 16 == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c;
+      if (!row_ok || col0 >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias != nullptr && (col0 + j) < p.N) x += p.bias[col0 + j];
+        v[j] = apply_act(x, p.act);
+      }
+      const bool full = (col0 + 32 <= p.N);
+      if (p.atomic_out) {
+        float* d = reinterpret_cast<float*>(drow) + col0;
+        if (full && vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + j), "f"(v[j]), "f"(v[j + 1]),
+                         "f"(v[j + 2]), "f"(v[j + 3])
+                         : "memory");
+        } else {
+          for (int j = 0; j < 32 && col0 + j < p.N; ++j) atomicAdd(d + j, v[j]);
+        }
+      } else if (p.out_fp32) {
+        float* d = reinterpret_cast<float*>(drow) + col0;
+        if (full && vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32 && col0 + j < p.N; ++j) d[j] = v[j];
+        }
+      } else {
+        __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(drow) + col0;
+        if (full && vec_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(v[j], v[j + 1]);
+            o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+            o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+            o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(d + j) = o;
+          }
+        } else {
+          for (int j = 0; j < 32 && col0 + j < p.N; ++j) d[j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BN);
+}
+
+
+// ---- runtime-depth pipeline + cluster split-K (DSMEM reduce) ----
+template <int BN, bool CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
@@ -154,7 +343,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = p.stages;
   const int ring_bytes = STAGES * L::STAGE_BYTES;
-  const int data_bytes = (p.cluster_k > 1 && L::PART_BYTES > ring_bytes) ? L::PART_BYTES : ring_bytes;
+  const int data_bytes = (CLUSTER && L::PART_BYTES > ring_bytes) ? L::PART_BYTES : ring_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + data_bytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
@@ -281,7 +470,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       tmem_ld_wait();
-      if (p.cluster_k > 1) {
+      if constexpr (CLUSTER) {
         float4* dst = reinterpret_cast<float4*>(part + lrow * L::PART_PITCH + c);
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -298,7 +487,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
 
-  if (p.cluster_k > 1) {
+  if constexpr (CLUSTER) {
     // ===================== cluster split-K: reduce the S partial tiles through DSMEM =====================
     const int S = p.cluster_k;
     cluster_sync_all();  // every CTA's partial tile is in its shared memory
@@ -366,6 +555,23 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
+template <int BN, int STAGES>
+static int launch_fixed(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
+                      cudaStream_t stream) {
+  constexpr int smem = STAGES * SmemLayout<BN>::STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_fixed_kernel<BN, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  cudaError_t le = launch_pdl(gemm_bf16_fixed_kernel<BN, STAGES>, grid, GEMM_THREADS, smem, stream, ta, tb, p);
+  if (le != cudaSuccess) return static_cast<int>(le);
+  return static_cast<int>(cudaGetLastError());
+}
+
+
 template <int BN>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
                       cudaStream_t stream) {
@@ -374,14 +580,28 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   constexpr int max_smem = max_stages * L::STAGE_BYTES + (2 * MAX_STAGES + 1) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         max_smem > L::PART_BYTES + 2048 ? max_smem : L::PART_BYTES + 2048);
+    const int cap = max_smem > L::PART_BYTES + 2048 ? max_smem : L::PART_BYTES + 2048;
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
   int ring = p.stages * L::STAGE_BYTES;
   if (p.cluster_k > 1 && L::PART_BYTES > ring) ring = L::PART_BYTES;
-  const int smem = ring + (2 * MAX_STAGES + 1) * 8 + 16 + 1024;
+  int smem = ring + (2 * MAX_STAGES + 1) * 8 + 16 + 1024;
+  // occupancy cap: CTAs of this kernel per SM (shared memory is the limiter we control)
+  static int max_ctas = -1;
+  if (max_ctas < 0) {
+    const char* e = std::getenv("BATON_GEMM_CTAS_PER_SM");
+    max_ctas = e != nullptr ? std::atoi(e) : 2;
+    if (max_ctas < 1) max_ctas = 1;
+  }
+  // atomic epilogues (wgrad) measured slower with co-resident CTAs: keep those at one CTA per SM
+  const int ctas_here = p.atomic_out ? 1 : max_ctas;
+  const int floor_smem = (227 * 1024) / (ctas_here + 1) + 1024;   // > 1/(ctas+1) of the SM
+  if (smem < floor_smem && floor_smem <= max_smem) smem = floor_smem;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -403,7 +623,8 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN>, ta, tb, p);
+  cudaError_t le = p.cluster_k > 1 ? cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, ta, tb, p)
+                                   : cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, false>, ta, tb, p);
   if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
@@ -464,7 +685,12 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
   const int max_stages = (bn == 256) ? 4 : (bn == 128 ? 6 : 8);
   p.stages = per < max_stages ? (per < 2 ? 2 : per) : max_stages;
   dim3 grid((N + bn - 1) / bn, (M + BM - 1) / BM, split_k);
-  if (bn == 256) return launch_cfg<256>(ta, tb, p, grid, stream);
-  if (bn == 128) return launch_cfg<128>(ta, tb, p, grid, stream);
-  return launch_cfg<64>(ta, tb, p, grid, stream);
+  if (cluster_k > 1) {
+    if (bn == 256) return launch_cfg<256>(ta, tb, p, grid, stream);
+    if (bn == 128) return launch_cfg<128>(ta, tb, p, grid, stream);
+    return launch_cfg<64>(ta, tb, p, grid, stream);
+  }
+  if (bn == 256) return launch_fixed<256, 4>(ta, tb, p, grid, stream);
+  if (bn == 128) return launch_fixed<128, 6>(ta, tb, p, grid, stream);
+  return launch_fixed<64, 8>(ta, tb, p, grid, stream);
 }

@@ -52,11 +52,18 @@ def pick_split_k(M: int, N: int, K: int, bn: int) -> int:
 
 def pick_cluster_k(M: int, N: int, K: int, bn: int) -> int:
     """Cluster split-K factor (1, 2, 4 or 8) for GEMMs with few output tiles and a long K."""
+    import os
     tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
     k_tiles = (K + 63) // 64
+    min_kt = int(os.environ.get("BATON_GEMM_CLUSTER_MIN_KT", "4"))   # k tiles each CTA must keep
+    if min_kt <= 0 or k_tiles < 16:     # short main loops gain nothing (8192x64x576: 5.5 us plain vs 6.7 us split)
+        return 1
     best = 1
     for s in (2, 4, 8):
-        if tiles * s <= NUM_SMS and k_tiles >= 4 * s:
+        # measured on B200: clusters of 8 only pay off while they cover at most ~half the SMs
+        # (placement needs 8 free SMs inside one GPC); clusters of <= 4 are fine up to a full wave
+        cap = NUM_SMS // 2 if s == 8 else 128
+        if tiles * s <= cap and k_tiles >= min_kt * s:
             best = s
     return best
 
