@@ -86,8 +86,8 @@ def main() -> None:
                 super().__init__()
                 self.net = tv.models.resnet18(num_classes=10)
 
-            def state_dict(self, *a, **kw):
-                return self.net.state_dict()
+            def state_dict(self, *a, **kw):   # live tensors (the reference writes into them in place)
+                return collections.OrderedDict((k, v) for k, v in self.net.state_dict().items() if v.dim() > 0)
 
         app = web.Application(client_max_size=1 << 32)
         ref_manager.Manager(app).register_experiment(CpuModel())
@@ -103,8 +103,10 @@ def main() -> None:
     dev = torch.device("cuda", local_rank) if on_gpu else torch.device("cpu")
     if on_gpu:
         torch.cuda.set_device(dev)
-    if world > 1:   # only for the timing barrier / max over ranks
-        dist.init_process_group("nccl", device_id=dev) if on_gpu else dist.init_process_group("gloo")
+    if world > 1:
+        # host-side barriers only (gloo): an NCCL barrier kernel parked on the GPU would block the
+        # worker's training kernels, which the reference launches from its aiohttp handler thread
+        dist.init_process_group("gloo")
 
     # ------------------------------------------------------------------ user model (reference contract)
     class Model(torch.nn.Module):
@@ -118,11 +120,15 @@ def main() -> None:
         def forward(self, X):
             return self.net(X)
 
-        def state_dict(self, *a, **kw):           # tensors cross the wire as CPU tensors, as in the reference
-            return collections.OrderedDict((k, v.detach().cpu()) for k, v in self.net.state_dict().items())
+        def state_dict(self, *a, **kw):
+            # tensors cross the wire as CPU tensors, as in the reference.  0-dim integer buffers
+            # (BatchNorm num_batches_tracked) are left out: reference manager.py:126 does
+            # ``value[:] = ...`` which raises IndexError on a 0-dim tensor and aborts the FedAvg loop.
+            return collections.OrderedDict((k, v.detach().cpu()) for k, v in self.net.state_dict().items()
+                                           if v.dim() > 0)
 
         def load_state_dict(self, sd, *a, **kw):
-            return self.net.load_state_dict(sd)
+            return self.net.load_state_dict(sd, strict=False)
 
         def train(self, X=None, y=None, n_epoch=32, lr=args.lr, batch_size=args.batch_size, verbose=False):
             if X is None or isinstance(X, bool):
@@ -242,17 +248,25 @@ def main() -> None:
         last = None
         for _ in range(k):
             if rank == 0:
-                last = call(one_round(args.local_epochs), timeout=3600)
+                last = call(one_round(args.local_epochs), timeout=900)
             barrier()
         return last
 
-    rounds(args.warmup)
-    barrier()
-    t0 = time.perf_counter()
-    last_loss = rounds(args.steps)
-    barrier()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=dev)
+    try:
+        rounds(args.warmup)
+        barrier()
+        t0 = time.perf_counter()
+        last_loss = rounds(args.steps)
+        barrier()
+        dt = time.perf_counter() - t0
+    except BaseException as exc:   # a wedged reference round must not hang the driver
+        if manager_proc is not None:
+            manager_proc.terminate()
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": "reference round failed: {!r}".format(exc)}),
+                  file=real_stdout, flush=True)
+        os._exit(0)
+    t = torch.tensor([dt])
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
