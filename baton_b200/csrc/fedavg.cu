@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(con
   const float my_n = a.n_samples[a.rank];
   const size_t esz = WIRE_BF16 ? 2 : 4;
   uint8_t* my_wire = reinterpret_cast<uint8_t*>(a.wire[a.rank]);
+  const float* __restrict__ theta_r = a.theta;
+  const float* __restrict__ global_r = a.global_w;
 
   // ---------------------------------------------------------------- phase 0: pack (+ prescale) + cast
   // P2P mode applies w_k on the reader side (the upload keeps full wire precision); NVLS mode needs
@@ -150,19 +152,39 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(con
         if (t >= n_tiles) break;
         const long long base = t * T;
         const int len = static_cast<int>((n - base) < T ? (n - base) : T);
-        for (int i = threadIdx.x * VEC; i < len; i += FEDAVG_THREADS * VEC) {
-          float f[VEC];
+        constexpr int STEP = FEDAVG_THREADS * VEC;
+        for (int i0 = threadIdx.x * VEC; i0 < len; i0 += 2 * STEP) {
+          // two independent 16 B wire vectors per trip, every load issued before the first store
+          float4 th[2][VEC / 4], gg[2][VEC / 4];
 #pragma unroll
-          for (int j = 0; j < VEC; j += 4) {
-            float4 th = *reinterpret_cast<const float4*>(a.theta + base + i + j);
-            if (a.delta) {
-              const float4 g = *reinterpret_cast<const float4*>(a.global_w + base + i + j);
-              th.x -= g.x; th.y -= g.y; th.z -= g.z; th.w -= g.w;
+          for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * STEP;
+            if (i < len) {
+#pragma unroll
+              for (int j = 0; j < VEC; j += 4) {
+                th[u][j >> 2] = __ldcs(reinterpret_cast<const float4*>(theta_r + base + i + j));
+                if (a.delta) gg[u][j >> 2] = __ldcs(reinterpret_cast<const float4*>(global_r + base + i + j));
+              }
             }
-            f[j] = th.x * pack_scale; f[j + 1] = th.y * pack_scale;
-            f[j + 2] = th.z * pack_scale; f[j + 3] = th.w * pack_scale;
           }
-          *reinterpret_cast<uint4*>(my_wire + (base + i) * esz) = W::pack(f);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = i0 + u * STEP;
+            if (i < len) {
+              float f[VEC];
+#pragma unroll
+              for (int j = 0; j < VEC; j += 4) {
+                float4 t4 = th[u][j >> 2];
+                if (a.delta) {
+                  const float4 g = gg[u][j >> 2];
+                  t4.x -= g.x; t4.y -= g.y; t4.z -= g.z; t4.w -= g.w;
+                }
+                f[j] = t4.x * pack_scale; f[j + 1] = t4.y * pack_scale;
+                f[j + 2] = t4.z * pack_scale; f[j + 3] = t4.w * pack_scale;
+              }
+              *reinterpret_cast<uint4*>(my_wire + (base + i) * esz) = W::pack(f);
+            }
+          }
         }
       }
     }
@@ -247,24 +269,44 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(con
       if (t >= n_tiles) break;
       const long long base = t * T;
       const int len = static_cast<int>((n - base) < T ? (n - base) : T);
-      for (int i = threadIdx.x * VEC; i < len; i += FEDAVG_THREADS * VEC) {
-        float f[VEC];
-        W::unpack(ld_volatile_v4(my_wire + (base + i) * esz), f);
+      constexpr int STEP = FEDAVG_THREADS * VEC;
+      for (int i0 = threadIdx.x * VEC; i0 < len; i0 += 2 * STEP) {
+        uint4 wv[2];
+        float4 gg[2][VEC / 4];
 #pragma unroll
-        for (int j = 0; j < VEC; j += 4) {
-          float4 nw = make_float4(f[j] * apply_scale, f[j + 1] * apply_scale, f[j + 2] * apply_scale,
-                                  f[j + 3] * apply_scale);
-          if (a.delta) {
-            const float4 g = *reinterpret_cast<const float4*>(a.global_w + base + i + j);
-            nw.x += g.x; nw.y += g.y; nw.z += g.z; nw.w += g.w;
+        for (int u = 0; u < 2; ++u) {
+          const int i = i0 + u * STEP;
+          if (i < len) {
+            wv[u] = ld_volatile_v4(my_wire + (base + i) * esz);
+            if (a.delta) {
+#pragma unroll
+              for (int j = 0; j < VEC; j += 4) gg[u][j >> 2] = *reinterpret_cast<const float4*>(a.global_w + base + i + j);
+            }
           }
-          if (a.global_w != nullptr) *reinterpret_cast<float4*>(a.global_w + base + i + j) = nw;
-          *reinterpret_cast<float4*>(a.theta + base + i + j) = nw;
-          if (a.momentum != nullptr && base + i + j < a.n_momentum)
-            *reinterpret_cast<float4*>(a.momentum + base + i + j) = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.theta_bf16 != nullptr) {
-            const uint2 o = make_uint2(pack_bf16x2(nw.x, nw.y), pack_bf16x2(nw.z, nw.w));
-            *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.theta_bf16) + (base + i + j) * 2) = o;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = i0 + u * STEP;
+          if (i < len) {
+            float f[VEC];
+            W::unpack(wv[u], f);
+#pragma unroll
+            for (int j = 0; j < VEC; j += 4) {
+              float4 nw = make_float4(f[j] * apply_scale, f[j + 1] * apply_scale, f[j + 2] * apply_scale,
+                                      f[j + 3] * apply_scale);
+              if (a.delta) {
+                const float4 g = gg[u][j >> 2];
+                nw.x += g.x; nw.y += g.y; nw.z += g.z; nw.w += g.w;
+              }
+              if (a.global_w != nullptr) *reinterpret_cast<float4*>(a.global_w + base + i + j) = nw;
+              *reinterpret_cast<float4*>(a.theta + base + i + j) = nw;
+              if (a.momentum != nullptr && base + i + j < a.n_momentum)
+                *reinterpret_cast<float4*>(a.momentum + base + i + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (a.theta_bf16 != nullptr) {
+                const uint2 o = make_uint2(pack_bf16x2(nw.x, nw.y), pack_bf16x2(nw.z, nw.w));
+                *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.theta_bf16) + (base + i + j) * 2) = o;
+              }
+            }
           }
         }
       }

@@ -32,7 +32,7 @@ def _align(x: int, a: int) -> int:
 
 class FedAvgSession:
     def __init__(self, arena: ParamArena, group=None, *, wire_dtype: str = "bf16", mode: str = "delta",
-                 nvls: "bool | str" = "auto", n_ctas: int = 64, tile_elems: int = 4096, timeout_log2: int = 0,
+                 nvls: "bool | str" = "auto", n_ctas: int = 148, tile_elems: int = 0, timeout_log2: int = 0,
                  reset_momentum: bool = True, tile_flags: bool = False):
         from ..ops._ext import load
         self._C = load()
@@ -61,8 +61,11 @@ class FedAvgSession:
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.loss_local = torch.zeros(MAX_LOSS, dtype=torch.float32, device=self.device)
         self.loss_out = torch.zeros(MAX_LOSS, dtype=torch.float32, device=self.device)
-        n_tiles = (arena.n + self.tile_elems - 1) // self.tile_elems
+        # tile_elems == 0: sized per launch so that every CTA of every live rank owns ~one tile
+        self.min_tile = 1024
+        n_tiles = (arena.n + self.min_tile - 1) // self.min_tile
         self.tile_flags = torch.zeros(n_tiles, dtype=torch.int32, device=self.device) if tile_flags else None
+        self.last_tile_elems = self.tile_elems or self.min_tile
         # a high-priority stream lets the collective's CTAs become resident ahead of a flag-gated
         # GEMM that is launched right behind it on the compute stream
         self.stream = torch.cuda.Stream(device=self.device, priority=-1) if self.device.type == "cuda" else None
@@ -96,6 +99,12 @@ class FedAvgSession:
             self.loss_local.zero_()
             self.loss_local[:k].copy_(torch.tensor([float(x) for x in loss_history[:k]]), non_blocking=True)
         a = self.arena
+        if self.tile_elems:
+            tile = self.tile_elems
+        else:   # one tile per (live rank, CTA): n / (A * G), rounded up to a multiple of 8 elements
+            per = -(-a.n // (len(alive) * self.n_ctas))
+            tile = max(self.min_tile, (per + 7) // 8 * 8)
+        self.last_tile_elems = tile
         flag_value = self.rounds + 1
         cur = torch.cuda.current_stream(self.device)
         stream = self.stream if on_side_stream else cur
@@ -112,8 +121,8 @@ class FedAvgSession:
                 self.loss_local, self.symm.peer_ptrs(self.off_loss), self.loss_out,
                 counts, from_flags, mask, self.rank, world, self.wire_bf16, self.delta,
                 bool(self.use_nvls and len(alive) == world), self.epoch,
-                self.tile_flags, flag_value, self.tile_elems, self.n_ctas, self.timeout_log2, self.status)
-        self.epoch = (self.epoch + 3) & 0x7FFFFFFF
+                self.tile_flags, flag_value, tile, self.n_ctas, self.timeout_log2, self.status)
+        self.epoch = (self.epoch + 3) & 0xFFFFFFFF     # uint32 wrap: the kernel compares signed differences
         self.rounds += 1
         self._side_pending = on_side_stream
 
@@ -147,7 +156,7 @@ class FedAvgSession:
                 if s.is_param and self.arena._owner(name) is module and name.endswith(".bias"):
                     bias_off = s.offset
         module.flags_cfg = {"flags": self.tile_flags, "epoch": self.rounds, "elem_off": slot.offset,
-                            "tile_elems": self.tile_elems, "bias_off": bias_off}
+                            "tile_elems": self.last_tile_elems, "bias_off": bias_off}
 
     def reduced_loss(self, n_epoch: int) -> List[float]:
         return self.loss_out[: min(n_epoch, MAX_LOSS)].tolist()

@@ -29,7 +29,7 @@ tr = GraphedLocalSGD(m, arena, loss="ce", use_graph=False)
 X, y = image_shard(ShardSpec(0, torch.full((10,), 0.1), args.batch_size * args.steps), dtype=torch.bfloat16)
 X, y = X.to(dev), y.to(dev)
 tr.run(X, y, n_epoch=1, lr=0.05, batch_size=args.batch_size)
-sess = FedAvgSession(arena, n_ctas=64)
+sess = FedAvgSession(arena)
 for _ in range(args.agg):
     sess.aggregate(my_n=1.0)
 torch.cuda.synchronize()
