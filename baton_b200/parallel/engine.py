@@ -66,6 +66,7 @@ class FederatedEngine:
         self._stage: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._acc = None
         self.last_losses_dev = None
+        self.samples_trained = 0          # samples this rank pushed through local SGD (per epoch)
 
     # ------------------------------------------------------------------ data staging
     def stage(self, X_host: torch.Tensor, y_host: torch.Tensor, slot: int = 0):
@@ -141,6 +142,7 @@ class FederatedEngine:
             if losses_dev is not None and total_n:
                 losses_dev = losses_dev / total_n
         self.last_losses_dev = losses_dev
+        self.samples_trained += int(total_n)
         loss_for_wire = None
         if losses_dev is not None:
             steps = max(1, self.trainer.last_steps)

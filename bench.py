@@ -46,6 +46,9 @@ def parse_args(argv=None):
     ap.add_argument("--n-ctas", type=int, default=148)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nvls", default="auto")
+    ap.add_argument("--logical-clients", type=int, default=0,
+                    help="> n_gpus: time-slice this many logical clients over the GPUs (sampling sweep config)")
+    ap.add_argument("--sample-k", type=int, default=None, help="logical clients sampled per round")
     return ap.parse_args(argv)
 
 
@@ -134,13 +137,21 @@ def main(argv=None):
     eng = FederatedEngine(model, dev, backend=args.backend, lr=args.lr, batch_size=args.batch_size,
                           momentum=args.momentum, wire_dtype=args.wire, n_ctas=args.n_ctas,
                           use_graph=not args.no_graph, nvls=(args.nvls if args.nvls == "auto" else args.nvls == "1"),
-                          name=args.model)
+                          name=args.model, logical_clients=args.logical_clients, sample_k=args.sample_k, seed=5)
 
     # private synthetic non-IID shard of this client, in pinned host memory (bf16 NHWC) + resident copy
     num_classes = model.fc.out_features
-    spec = dirichlet_label_shards(max(world, 1), num_classes, args.samples, alpha=args.alpha, seed=11)[rank]
-    X_host, y_host = image_shard(spec, seed=3, dtype=torch.bfloat16, pin=True)
-    X_dev, y_dev = X_host.to(dev), y_host.to(dev)
+    n_logical = args.logical_clients if args.logical_clients > world else world
+    specs = dirichlet_label_shards(n_logical, num_classes, args.samples, alpha=args.alpha, seed=11)
+    mine = [c for c in range(n_logical) if c % world == rank]
+    host_shards = {c: image_shard(specs[c], seed=3, dtype=torch.bfloat16, pin=True) for c in mine}
+    dev_shards = {c: (x.to(dev), y.to(dev)) for c, (x, y) in host_shards.items()}
+    X_host, y_host = host_shards[mine[0]]
+    X_dev, y_dev = dev_shards[mine[0]]
+    if eng.logical_clients:      # shards are addressed by logical client id
+        X_dev = y_dev = None
+        resident = lambda cid: dev_shards[cid]      # noqa: E731
+        pinned = lambda cid: host_shards[cid]       # noqa: E731
     h2d = FederatedEngine.h2d_bytes(X_host, y_host)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -161,7 +172,14 @@ def main(argv=None):
         return last
 
     # ---- warm-up (captures the epoch graph, warms NVLink mappings) -------------------------------
-    run((X_dev, y_dev), max(args.warmup, 3), read_loss=False)
+    res_shard = resident if eng.logical_clients else (X_dev, y_dev)
+    pin_shard = pinned if eng.logical_clients else (X_host, y_host)
+    if eng.logical_clients:      # capture the epoch graph of every hosted logical client up front
+        for c in mine:
+            eng.trainer.run(*dev_shards[c], n_epoch=1, return_device=True, **eng.hp)
+            eng.arena.theta.copy_(eng.arena.global_w)
+            eng.arena.sync_shadow()
+    run(res_shard, max(args.warmup, 3), read_loss=False)
     barrier()
 
     # ---- (a) device-timed: resident shard, no host traffic in the loop ---------------------------
@@ -174,7 +192,9 @@ def main(argv=None):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    run((X_dev, y_dev), args.steps, read_loss=False, timers=ev)
+    n0 = eng.samples_trained
+    run(res_shard, args.steps, read_loss=False, timers=ev)
+    trained = eng.samples_trained - n0
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
@@ -197,21 +217,24 @@ def main(argv=None):
     agg_us = min(agg_ms) * 1e3
 
     # ---- (b) end to end through the public API: pinned H2D every round + loss D2H every round ----
-    run((X_host, y_host), 2, read_loss=True)
+    run(pin_shard, 2, read_loss=True)
     barrier()
+    n0 = eng.samples_trained
     t0 = time.perf_counter()
-    res = run((X_host, y_host), args.steps, read_loss=True)
+    res = run(pin_shard, args.steps, read_loss=True)
     barrier()
     e2e_s = time.perf_counter() - t0
+    trained_e2e = eng.samples_trained - n0
 
     t = torch.tensor([dev_ms, e2e_s * 1e3, agg_us], device=dev, dtype=torch.float64)
+    cnt = torch.tensor([trained, trained_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, e2e_ms, agg_us = [float(x) for x in t.tolist()]
     if rank == 0:
-        per_round = world * args.samples * args.local_epochs
-        value = per_round * args.steps / (dev_ms / 1e3)
-        e2e_value = per_round * args.steps / (e2e_ms / 1e3)
+        value = float(cnt[0]) * args.local_epochs / (dev_ms / 1e3)          # samples actually trained, whole box
+        e2e_value = float(cnt[1]) * args.local_epochs / (e2e_ms / 1e3)
         wire_bytes = eng.session.wire_bytes()
         out = {
             "metric": "federated local samples/sec (whole box), ResNet-18 FedAvg, synthetic non-IID 32x32 shards",
@@ -225,7 +248,8 @@ def main(argv=None):
                        "backend": args.backend, "wire_dtype": args.wire, "upload": "delta",
                        "nvls": bool(getattr(eng.session, "use_nvls", False)),
                        "cuda_graph": not args.no_graph, "optimizer": "sgd(lr={}, momentum={})".format(args.lr, args.momentum),
-                       "l2": "256 MiB memset between rounds (flush)", "dirichlet_alpha": args.alpha},
+                       "l2": "256 MiB memset between rounds (flush)", "dirichlet_alpha": args.alpha,
+                       "logical_clients": n_logical, "sampled_per_round": args.sample_k or n_logical},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * args.local_epochs,
