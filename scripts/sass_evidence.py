@@ -1,0 +1,40 @@
+"""Regenerate docs/sass/: full SASS of the two headline kernels and a per-kernel table of the
+Blackwell-specific mnemonics (UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG = TMA, LDGMC =
+multimem.ld_reduce, ...).  Runs on a GPU-less host: cuobjdump only reads the objects."""
+import collections
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "baton_b200", "csrc", "build")
+OUT = os.path.join(ROOT, "docs", "sass")
+KEY = re.compile(r"\b(UTC[A-Z0-9]+(?:\.[A-Z0-9_]+)*|UTMA[A-Z]+(?:\.[A-Z0-9_]+)*|LDTM(?:\.[A-Za-z0-9_]+)*|STTM|UBLKCP|"
+                 r"SYNCS(?:\.[A-Z0-9_]+)*|LDGMC(?:\.[A-Z0-9_]+)*|UCGABAR[A-Z_.]*|MAPA(?:\.[A-Z0-9_]+)*|"
+                 r"LDS(?:\.[A-Z0-9_]+)*|RED(?:\.[A-Z0-9_]+)+|[A-Z]+\.E\.[0-9A-Z.]*SYS|HMMA[A-Z0-9_.]*|ACQBULK|"
+                 r"ATOMG?(?:\.[A-Z0-9_]+)*|ELECT|CCTL[A-Z.]*|MEMBAR[A-Z.]*)")
+os.makedirs(OUT, exist_ok=True)
+lines = ["# SASS evidence per kernel (`cuobjdump -sass`, sm_100a)", "",
+         "`UTCHMMA` = tcgen05.mma kind::f16, `UTCBAR` = tcgen05.commit, `LDTM` = tcgen05.ld, `UTMALDG` = TMA tiled",
+         "load, `SYNCS.*` = mbarrier, `LDGMC` = multimem.ld_reduce (NVLS in-switch reduction), `UCGABAR` = cluster",
+         "barrier, `*.SYS` = system-scope (cross-GPU) loads/stores.  Full listings: `gemm_tcgen05.sass`,",
+         "`fedavg.sass`.", ""]
+for f in ["gemm_tcgen05", "fedavg", "elementwise", "conv", "norm", "loss", "gemm_simt"]:
+    obj = os.path.join(BUILD, f + ".o")
+    if not os.path.exists(obj):
+        continue
+    txt = subprocess.run(["cuobjdump", "-sass", obj], stdout=subprocess.PIPE, text=True).stdout
+    if f in ("gemm_tcgen05", "fedavg"):
+        open(os.path.join(OUT, f + ".sass"), "w").write(txt)
+    lines.append("## {}.cu".format(f))
+    for fn in re.split(r"\n\s*Function : ", txt)[1:]:
+        name = fn.split("\n", 1)[0].strip()
+        n_instr = len(re.findall(r"/\*[0-9a-f]{4}\*/", fn))
+        c = collections.Counter(m.group(1) for m in KEY.finditer(fn))
+        demangled = subprocess.run(["c++filt", name], stdout=subprocess.PIPE, text=True).stdout.strip()
+        lines.append("- `{}` ({} instructions)".format(demangled[:120], n_instr))
+        if c:
+            lines.append("    " + ", ".join("{} x{}".format(k, v) for k, v in sorted(c.items())))
+    lines.append("")
+open(os.path.join(OUT, "MNEMONICS.md"), "w").write("\n".join(lines))
+print("wrote", OUT)
