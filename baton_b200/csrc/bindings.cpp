@@ -47,6 +47,19 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::opt
         "gemm_bf16");
 }
 
+void gemm_batched(const at::Tensor& a, const at::Tensor& b, at::Tensor d, int64_t M, int64_t N, int64_t K, int64_t lda,
+                  int64_t ldb, int64_t ldd, bool a_mn, bool b_mn, int64_t act, double alpha, int64_t n_outer,
+                  int64_t n_inner, int64_t a_outer, int64_t a_inner, int64_t b_outer, int64_t b_inner, int64_t d_outer,
+                  int64_t d_inner, bool accumulate) {
+  CHECK_CUDA(a); CHECK_CUDA(b); CHECK_CUDA(d);
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm operands must be bf16");
+  const c10::cuda::CUDAGuard guard(a.device());
+  check(b200_gemm_bf16_batched(cptr(a), cptr(b), ptr(d), M, N, K, lda, ldb, ldd, a_mn, b_mn,
+                               d.scalar_type() == at::kFloat, act, static_cast<float>(alpha), n_outer, n_inner, a_outer,
+                               a_inner, b_outer, b_inner, d_outer, d_inner, accumulate, cur_stream()),
+        "gemm_bf16_batched");
+}
+
 void fused_sgd(at::Tensor w, at::Tensor g, const std::optional<at::Tensor>& mom, const std::optional<at::Tensor>& wb,
                const at::Tensor& hyper, bool zero_grad, bool nesterov) {
   CHECK_CUDA(w);
@@ -132,6 +145,14 @@ void gelu_bwd(const at::Tensor& x, const at::Tensor& dy, at::Tensor dx) {
   CHECK_CUDA(x);
   const c10::cuda::CUDAGuard guard(x.device());
   check(b200_gelu_bwd_bf16(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel(), cur_stream()), "gelu_bwd");
+}
+void embedding_bwd(const at::Tensor& dy, const at::Tensor& idx, at::Tensor grad) {
+  CHECK_CUDA(dy);
+  TORCH_CHECK(dy.scalar_type() == at::kBFloat16 && grad.scalar_type() == at::kFloat && idx.scalar_type() == at::kLong);
+  const c10::cuda::CUDAGuard guard(dy.device());
+  check(b200_embedding_bwd(dy.data_ptr(), reinterpret_cast<const long long*>(idx.data_ptr<int64_t>()),
+                           grad.data_ptr<float>(), idx.numel(), static_cast<int>(dy.size(-1)), cur_stream()),
+        "embedding_bwd");
 }
 void pad_rows(const at::Tensor& s, at::Tensor d, int64_t rows, int64_t k, int64_t kp) {
   CHECK_CUDA(s);
@@ -347,6 +368,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "baton_b200 sm_100a kernels";
   m.attr("MAX_RANKS") = B200_MAX_RANKS;
   m.def("gemm", &gemm);
+  m.def("gemm_batched", &gemm_batched);
   m.def("fused_sgd", &fused_sgd);
   m.def("weighted_sum", &weighted_sum);
   m.def("cast", &cast);
@@ -357,6 +379,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gelu", &gelu);
   m.def("gelu_bwd", &gelu_bwd);
   m.def("pad_rows", &pad_rows);
+  m.def("embedding_bwd", &embedding_bwd);
   m.def("fedavg_allreduce", &fedavg_allreduce);
   m.def("flag_barrier", &flag_barrier);
   m.def("im2col", &im2col);

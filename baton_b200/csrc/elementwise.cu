@@ -283,6 +283,25 @@ pad_rows_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__
   }
 }
 
+// embedding backward: grad_table[idx[r], :] += dy[r, :]  (fp32 atomics; rows of 8-element vectors)
+__global__ void __launch_bounds__(EW_THREADS)
+embedding_bwd_kernel(const uint4* __restrict__ dy, const long long* __restrict__ idx, float* __restrict__ grad,
+                     long long n_rows, int row_vecs) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const long long total = n_rows * row_vecs;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / row_vecs;
+    const int c = static_cast<int>(i - r * row_vecs);
+    const uint4 v = dy[i];
+    float* g = grad + (idx[r] * row_vecs + c) * 8;
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), cc = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + 4), "f"(cc.x), "f"(cc.y), "f"(d.x), "f"(d.y) : "memory");
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -375,5 +394,14 @@ extern "C" int b200_pad_rows_bf16(const void* src, void* dst, long long rows, in
   if (rows <= 0) return 0;
   launch_pdl(pad_rows_kernel, ew_grid(rows * kp), EW_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(src),
                                                                  reinterpret_cast<__nv_bfloat16*>(dst), rows, k, kp);
+  RET_LAST();
+}
+
+extern "C" int b200_embedding_bwd(const void* dy, const long long* idx, float* grad, long long n_rows, int width,
+                                  cudaStream_t stream) {
+  if (n_rows <= 0) return 0;
+  if (width % 8) return -2;
+  launch_pdl(embedding_bwd_kernel, ew_grid(n_rows * (width / 8)), EW_THREADS, 0, stream,
+             reinterpret_cast<const uint4*>(dy), idx, grad, n_rows, width / 8);
   RET_LAST();
 }

@@ -108,7 +108,7 @@ struct Wire<false> {  // 4 fp32 per 16 B
 };
 
 template <bool WIRE_BF16>
-__global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(const __grid_constant__ FedAvgArgs a) {
+__global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(const __grid_constant__ FedAvgArgs a) {
   using W = Wire<WIRE_BF16>;
   constexpr int VEC = W::VEC;
   const int G = gridDim.x;
@@ -221,24 +221,27 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 1) fedavg_allreduce_kernel(con
         out = W::mc_reduce(reinterpret_cast<const uint8_t*>(a.wire_mc) + off);  // the switch adds the replicas
         multimem_st_v4(reinterpret_cast<uint8_t*>(a.wire_mc) + off, out);       // the switch replicates the store
       } else {
-        // issue all peer loads first (memory-level parallelism), then accumulate in fixed rank
-        // order so the result is bitwise identical on every run
-        uint4 v[B200_MAX_RANKS];
-#pragma unroll
-        for (int k = 0; k < B200_MAX_RANKS; ++k)
-          if (k < A && s_w[k] != 0.f) v[k] = ld_volatile_v4(s_wire[k] + off);
+        // peers in groups of 8 (one NVSwitch box): issue the group's loads first (memory-level
+        // parallelism), then accumulate in fixed rank order so the result is bitwise reproducible
         float acc[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+#pragma unroll 1
+        for (int k0 = 0; k0 < A; k0 += 8) {
+          uint4 v[8];
 #pragma unroll
-        for (int k = 0; k < B200_MAX_RANKS; ++k) {
-          if (k < A) {
-            const float w = s_w[k];
-            if (w != 0.f) {
-              float f[VEC];
-              W::unpack(v[k], f);
+          for (int k = 0; k < 8; ++k)
+            if (k0 + k < A && s_w[k0 + k] != 0.f) v[k] = ld_volatile_v4(s_wire[k0 + k] + off);
 #pragma unroll
-              for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, f[j], acc[j]);
+          for (int k = 0; k < 8; ++k) {
+            if (k0 + k < A) {
+              const float w = s_w[k0 + k];
+              if (w != 0.f) {
+                float f[VEC];
+                W::unpack(v[k], f);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, f[j], acc[j]);
+              }
             }
           }
         }

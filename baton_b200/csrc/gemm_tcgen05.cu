@@ -57,6 +57,10 @@ struct GemmParams {
   long long flag_bias_off;     // arena element offset of bias[0], or -1
   long long ldb;               // row pitch of B (elements)
   float alpha;
+  // strided-batched mode (attention): blockIdx.z = outer * batch_inner + inner; operands come from
+  // 4-D tensor maps (col, row, inner, outer); D is offset by outer * d_outer + inner * d_inner elements
+  int batched, batch_inner;
+  long long d_outer, d_inner;
 };
 
 template <int BN>
@@ -163,7 +167,9 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int m0 = blockIdx.y * BM;
   const int n0 = blockIdx.x * BN;
   const int k_tiles_total = (p.K + BK - 1) / BK;
-  const int kt_begin = blockIdx.z * p.k_tiles_per_split;
+  const int bz_outer = p.batched ? static_cast<int>(blockIdx.z) / p.batch_inner : 0;
+  const int bz_inner = p.batched ? static_cast<int>(blockIdx.z) % p.batch_inner : 0;
+  const int kt_begin = p.batched ? 0 : blockIdx.z * p.k_tiles_per_split;
   int kt_end = kt_begin + p.k_tiles_per_split;
   if (kt_end > k_tiles_total) kt_end = k_tiles_total;
   const int num_kt = kt_end - kt_begin;  // host guarantees >= 1 for every launched z
@@ -220,6 +226,22 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint8_t* sb = sa + L::A_BYTES;
         const int k0 = (kt_begin + i) * BK;
         mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        if (p.batched) {
+          if (!p.a_mn) {
+            tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, bz_inner, bz_outer);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_4d(sa + j * 8192, &tmA, &full_bar[s], m0 + j * 64, k0, bz_inner, bz_outer);
+          }
+          if (!p.b_mn) {
+            tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, bz_inner, bz_outer);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_4d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0, bz_inner, bz_outer);
+          }
+        } else {
         if (!p.a_mn) {
           tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box [64 k][128 rows]
         } else {
@@ -232,6 +254,7 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0);
+        }
         }
       }
     }
@@ -270,7 +293,9 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int row = m0 + q * 32 + static_cast<int>(lane_id());
     const bool row_ok = row < p.M;
     const size_t elt = p.out_fp32 ? 4 : 2;
-    uint8_t* drow = reinterpret_cast<uint8_t*>(p.D) + static_cast<size_t>(row) * p.ldd * elt;
+    uint8_t* drow = reinterpret_cast<uint8_t*>(p.D) +
+                    (static_cast<size_t>(row) * p.ldd + static_cast<size_t>(bz_outer) * p.d_outer +
+                     static_cast<size_t>(bz_inner) * p.d_inner) * elt;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * elt) % 16 == 0);
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
@@ -555,6 +580,23 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, long lon
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
+// 4-D bf16 tensor map: [outer][inner][rows][cols] with element strides; box = [box_cols, box_rows, 1, 1]
+static int make_map4(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, long long inner,
+                     long long s_inner, long long outer, long long s_outer, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return -1;
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(inner),
+                        static_cast<cuuint64_t>(outer)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(s_inner) * 2,
+                        static_cast<cuuint64_t>(s_outer) * 2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
 template <int BN, int STAGES>
 static int launch_fixed(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
                       cudaStream_t stream) {
@@ -681,6 +723,7 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
   p.tile_flags = tile_flags; p.flag_epoch = flag_epoch; p.alpha = alpha;
   p.flag_elem_off = flag_elem_off; p.flag_tile_elems = flag_tile_elems; p.ldb = ldb;
   p.flag_bias_off = (tile_flags != nullptr && bias != nullptr) ? flag_bias_off : -1;
+  p.batched = 0; p.batch_inner = 1; p.d_outer = 0; p.d_inner = 0;
   if (p.atomic_out && (!out_fp32 || bias != nullptr || act != 0)) return -3;
   const int max_stages = (bn == 256) ? 4 : (bn == 128 ? 6 : 8);
   p.stages = per < max_stages ? (per < 2 ? 2 : per) : max_stages;
@@ -690,6 +733,48 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
     if (bn == 128) return launch_cfg<128>(ta, tb, p, grid, stream);
     return launch_cfg<64>(ta, tb, p, grid, stream);
   }
+  if (bn == 256) return launch_fixed<256, 4>(ta, tb, p, grid, stream);
+  if (bn == 128) return launch_fixed<128, 6>(ta, tb, p, grid, stream);
+  return launch_fixed<64, 8>(ta, tb, p, grid, stream);
+}
+
+// Strided-batched GEMM (attention): for z = outer * n_inner + inner
+//     D[z] = act(alpha * A[z] B[z]^T),  X[z] = X + outer * x_outer + inner * x_inner   (element strides)
+// Same operand-major conventions as b200_gemm_bf16; every stride must be a multiple of 8 elements.
+extern "C" int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int M, int N, int K, long long lda,
+                                      long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act,
+                                      float alpha, int n_outer, int n_inner, long long a_outer, long long a_inner,
+                                      long long b_outer, long long b_inner, long long d_outer, long long d_inner,
+                                      int accumulate, cudaStream_t stream) {
+  using namespace b200;
+  if (M <= 0 || N <= 0 || K <= 0 || n_outer <= 0 || n_inner <= 0) return 0;
+  if ((lda % 8) || (ldb % 8) || (a_outer % 8) || (a_inner % 8) || (b_outer % 8) || (b_inner % 8) ||
+      (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
+    return -2;
+  // degenerate strides (size-1 dims) still need a non-zero multiple-of-16-byte stride for the encoder
+  auto fix = [](long long s) { return s > 0 ? s : 8; };
+  const int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn)
+    rc = make_map4(&ta, a, M, K, lda, n_inner, fix(a_inner), n_outer, fix(a_outer), BK, BM);
+  else
+    rc = make_map4(&ta, a, K, M, lda, n_inner, fix(a_inner), n_outer, fix(a_outer), 64, BK);
+  if (rc) return rc;
+  if (!b_mn)
+    rc = make_map4(&tb, b, N, K, ldb, n_inner, fix(b_inner), n_outer, fix(b_outer), BK, bn);
+  else
+    rc = make_map4(&tb, b, K, N, ldb, n_inner, fix(b_inner), n_outer, fix(b_outer), 64, BK);
+  if (rc) return rc;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.D = d; p.ldd = ldd; p.bias = nullptr; p.out_fp32 = out_fp32; p.act = act;
+  p.a_mn = a_mn; p.b_mn = b_mn; p.k_tiles_per_split = (K + BK - 1) / BK; p.cluster_k = 1;
+  p.atomic_out = accumulate ? 1 : 0;
+  p.tile_flags = nullptr; p.flag_epoch = 0; p.alpha = alpha; p.flag_elem_off = 0; p.flag_tile_elems = 0;
+  p.ldb = ldb; p.flag_bias_off = -1; p.stages = 4;
+  p.batched = 1; p.batch_inner = n_inner; p.d_outer = d_outer; p.d_inner = d_inner;
+  if (p.atomic_out && !out_fp32) return -3;
+  dim3 grid((N + bn - 1) / bn, (M + BM - 1) / BM, n_outer * n_inner);
   if (bn == 256) return launch_fixed<256, 4>(ta, tb, p, grid, stream);
   if (bn == 128) return launch_fixed<128, 6>(ta, tb, p, grid, stream);
   return launch_fixed<64, 8>(ta, tb, p, grid, stream);

@@ -14,6 +14,10 @@ int b200_gemm_bf16(const void* a, const void* b, void* d, const float* bias, int
                    long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act, int split_k, int accumulate,
                    float alpha, const uint32_t* tile_flags, uint32_t flag_epoch, long long flag_elem_off, int flag_tile_elems,
                    long long flag_bias_off, int force_bn, cudaStream_t stream);
+int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int M, int N, int K, long long lda, long long ldb,
+                           long long ldd, int a_mn, int b_mn, int out_fp32, int act, float alpha, int n_outer,
+                           int n_inner, long long a_outer, long long a_inner, long long b_outer, long long b_inner,
+                           long long d_outer, long long d_inner, int accumulate, cudaStream_t stream);
 int b200_gemm_simt(const void* a, const void* b, void* d, const float* bias, int M, int N, int K, long long lda,
                    long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act, int accumulate,
                    float alpha, cudaStream_t stream);
@@ -35,6 +39,8 @@ int b200_add_bf16(const void* a, const void* b, void* out, long long n, int relu
 int b200_relu_bwd_bf16(const void* y, const void* dy, void* dx, long long n, cudaStream_t stream);
 int b200_gelu_bf16(const void* x, void* y, long long n, cudaStream_t stream);
 int b200_gelu_bwd_bf16(const void* x, const void* dy, void* dx, long long n, cudaStream_t stream);
+int b200_embedding_bwd(const void* dy, const long long* idx, float* grad, long long n_rows, int width,
+                       cudaStream_t stream);
 int b200_pad_rows_bf16(const void* src, void* dst, long long rows, int k, int kp, cudaStream_t stream);
 
 // ---- fedavg.cu

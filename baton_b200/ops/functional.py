@@ -258,3 +258,19 @@ def mse(pred: torch.Tensor, target: torch.Tensor, want_grad: bool = True):
     dp = torch.empty_like(pred) if want_grad else None
     load().mse(pred.contiguous(), target.contiguous().float(), dp, acc, 1.0 / pred.numel())
     return acc, dp
+
+
+# ---------------------------------------------------------------------------- batched GEMM / attention / embedding
+def gemm_batched(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int, K: int, lda: int, ldb: int,
+                 ldd: int, a_mn: bool, b_mn: bool, n_outer: int, n_inner: int, a_strides, b_strides, d_strides,
+                 alpha: float = 1.0, act: int = 0, accumulate: bool = False) -> torch.Tensor:
+    """Strided-batched tcgen05 GEMM over a two-level batch (outer, inner) = (batch, head): operands are
+    addressed through 4-D TMA tensor maps, so Q/K/V slices of a packed QKV buffer need no copies.
+    ``*_strides`` = (outer, inner) element strides; ``a``/``b``/``out`` give the base pointers."""
+    load().gemm_batched(a, b, out, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, alpha, n_outer, n_inner,
+                        a_strides[0], a_strides[1], b_strides[0], b_strides[1], d_strides[0], d_strides[1], accumulate)
+    return out
+
+
+def embedding_bwd_(dy2d: torch.Tensor, idx: torch.Tensor, grad_table: torch.Tensor) -> None:
+    load().embedding_bwd(dy2d, idx, grad_table)

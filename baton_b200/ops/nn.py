@@ -457,3 +457,99 @@ def mse_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     if not pred.is_cuda:
         return TF.mse_loss(pred.float(), target.float().reshape(pred.shape))
     return _MseFn.apply(pred.contiguous(), target.reshape(pred.shape))
+
+
+# ================================================================================ attention / embedding (BERT)
+class _AttnFn(torch.autograd.Function):
+    """Multi-head self-attention core on a packed ``qkv [B*S, 3*H*dh]`` buffer: four strided-batched
+    tcgen05 GEMMs + the row-softmax kernel forward, five GEMMs + softmax backward; Q/K/V and their
+    gradients are addressed in place through 4-D TMA maps (no head split / merge copies)."""
+
+    @staticmethod
+    def forward(ctx, qkv, B, S, H, dh):
+        D = H * dh
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        scores = torch.empty((B * H * S, S), dtype=BF16, device=qkv.device)
+        F.gemm_batched(q, k, scores, M=S, N=S, K=dh, lda=3 * D, ldb=3 * D, ldd=S, a_mn=False, b_mn=False,
+                       n_outer=B, n_inner=H, a_strides=(S * 3 * D, dh), b_strides=(S * 3 * D, dh),
+                       d_strides=(H * S * S, S * S), alpha=1.0 / math.sqrt(dh))
+        probs = torch.empty_like(scores)
+        load().softmax_fwd(scores, probs, B * H * S, S, 1.0)
+        out = torch.empty((B * S, D), dtype=BF16, device=qkv.device)
+        F.gemm_batched(probs, v, out, M=S, N=dh, K=S, lda=S, ldb=3 * D, ldd=D, a_mn=False, b_mn=True,
+                       n_outer=B, n_inner=H, a_strides=(H * S * S, S * S), b_strides=(S * 3 * D, dh),
+                       d_strides=(S * D, dh))
+        ctx.save_for_backward(qkv, probs)
+        ctx.dims = (B, S, H, dh)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, probs = ctx.saved_tensors
+        B, S, H, dh = ctx.dims
+        D = H * dh
+        dout = dout.contiguous()
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        dqkv = torch.empty_like(qkv)
+        dq, dk, dv = dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:]
+        bh = (H * S * S, S * S)
+        pk = (S * 3 * D, dh)
+        # dV = P^T dO
+        F.gemm_batched(probs, dout, dv, M=S, N=dh, K=S, lda=S, ldb=D, ldd=3 * D, a_mn=True, b_mn=True,
+                       n_outer=B, n_inner=H, a_strides=bh, b_strides=(S * D, dh), d_strides=pk)
+        # dP = dO V^T
+        dprobs = torch.empty_like(probs)
+        F.gemm_batched(dout, v, dprobs, M=S, N=S, K=dh, lda=D, ldb=3 * D, ldd=S, a_mn=False, b_mn=False,
+                       n_outer=B, n_inner=H, a_strides=(S * D, dh), b_strides=pk, d_strides=bh)
+        dscores = torch.empty_like(probs)
+        load().softmax_bwd(probs, dprobs, dscores, B * H * S, S, 1.0)
+        alpha = 1.0 / math.sqrt(dh)
+        # dQ = alpha dS K ; dK = alpha dS^T Q
+        F.gemm_batched(dscores, k, dq, M=S, N=dh, K=S, lda=S, ldb=3 * D, ldd=3 * D, a_mn=False, b_mn=True,
+                       n_outer=B, n_inner=H, a_strides=bh, b_strides=pk, d_strides=pk, alpha=alpha)
+        F.gemm_batched(dscores, q, dk, M=S, N=dh, K=S, lda=S, ldb=3 * D, ldd=3 * D, a_mn=True, b_mn=True,
+                       n_outer=B, n_inner=H, a_strides=bh, b_strides=pk, d_strides=pk, alpha=alpha)
+        return dqkv, None, None, None, None
+
+
+def attention(qkv: torch.Tensor, B: int, S: int, H: int, dh: int) -> torch.Tensor:
+    """``softmax(Q K^T / sqrt(dh)) V`` for packed ``qkv [B*S, 3*H*dh]`` -> ``[B*S, H*dh]``."""
+    if not qkv.is_cuda:
+        D = H * dh
+        q, k, v = (t.reshape(B, S, H, dh).transpose(1, 2) for t in qkv.split(D, dim=-1))
+        p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1)
+        return (p @ v).transpose(1, 2).reshape(B * S, D)
+    return _AttnFn.apply(qkv.contiguous(), B, S, H, dh)
+
+
+class _EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, table_bf16, ids):
+        ctx.save_for_backward(ids)
+        ctx.table = table
+        return F.gather_rows(table_bf16, ids)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        table = ctx.table
+        tgt = _grad_target(table)
+        g = None
+        if tgt is None:
+            g = tgt = torch.zeros_like(table, dtype=torch.float32)
+        F.embedding_bwd_(dy.contiguous(), ids, tgt)
+        return g, None, None
+
+
+class Embedding(nn.Module):
+    """Lookup in the bf16 shadow of an fp32 table; gradient scattered with fp32 atomics."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(num_embeddings, embedding_dim) * 0.02)
+
+    def forward(self, ids):
+        flat = ids.reshape(-1)
+        if not ids.is_cuda:
+            return TF.embedding(flat, self.weight)
+        return _EmbedFn.apply(self.weight, _shadow(self, "weight", self.weight), flat)

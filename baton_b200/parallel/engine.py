@@ -42,7 +42,7 @@ class RoundResult:
 class FederatedEngine:
     def __init__(self, model, device, *, backend: str = "fused", group=None, loss: str = "ce",
                  lr: float = 0.05, batch_size: int = 128, momentum: float = 0.0, weight_decay: float = 0.0,
-                 wire_dtype: str = "bf16", mode: str = "delta", n_ctas: int = 148, use_graph: bool = True,
+                 wire_dtype: str = "bf16", mode: str = "delta", n_ctas: int = 296, use_graph: bool = True,
                  logical_clients: int = 0, sample_k: Optional[int] = None, seed: int = 0, name: str = "exp",
                  nvls: "bool | str" = "auto", tile_flags: bool = False):
         self.device = torch.device(device)

@@ -23,7 +23,7 @@ from .arena import ParamArena
 from .symm import SymmetricBuffer
 
 MAX_LOSS = 64       # per-epoch loss slots carried through the collective
-MAX_CTAS = 148
+MAX_CTAS = 296      # 2 resident CTAs per SM
 
 
 def _align(x: int, a: int) -> int:
@@ -32,7 +32,7 @@ def _align(x: int, a: int) -> int:
 
 class FedAvgSession:
     def __init__(self, arena: ParamArena, group=None, *, wire_dtype: str = "bf16", mode: str = "delta",
-                 nvls: "bool | str" = "auto", n_ctas: int = 148, tile_elems: int = 0, timeout_log2: int = 0,
+                 nvls: "bool | str" = "auto", n_ctas: int = 296, tile_elems: int = 0, timeout_log2: int = 0,
                  reset_momentum: bool = True, tile_flags: bool = False):
         from ..ops._ext import load
         self._C = load()

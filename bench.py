@@ -43,7 +43,7 @@ def parse_args(argv=None):
     ap.add_argument("--alpha", type=float, default=0.5, help="Dirichlet label skew of the shards")
     ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--backend", default="fused", choices=["fused", "nccl"])
-    ap.add_argument("--n-ctas", type=int, default=148)
+    ap.add_argument("--n-ctas", type=int, default=296)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--nvls", default="auto")
     ap.add_argument("--logical-clients", type=int, default=0,
