@@ -553,6 +553,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn get_encode_fn() {
+  // cuTensorMapEncodeTiled is a DRIVER entry point: it needs a current context on the calling
+  // thread.  Autograd worker threads may not have touched the runtime yet -> bind the primary
+  // context once per thread (cudaFree(0) is the canonical no-op that does so).
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   static EncodeTiledFn fn = nullptr;
   if (fn == nullptr) {
     void* ptr = nullptr;

@@ -31,6 +31,34 @@ from ._ext import load
 BF16 = torch.bfloat16
 
 
+class _P:
+    """Opaque holder that carries a Parameter through ``Function.apply`` WITHOUT making it a
+    differentiable input.  In arena mode the backward kernels accumulate into ``param.grad`` themselves,
+    so autograd must not see the leaf: its cached AccumulateGrad node remembers the stream it was
+    created on, and merely scheduling it inside a CUDA-graph capture makes the engine record an event on
+    that (uncaptured) stream -> cudaErrorStreamCaptureIsolation.  A fresh zero-size ``anchor`` leaf
+    stands in so backward still runs for layers whose data input needs no gradient."""
+    __slots__ = ("p",)
+
+    def __init__(self, p):
+        self.p = p
+
+
+def _unwrap(v):
+    return v.p if isinstance(v, _P) else v
+
+
+def _wrap(param, x):
+    """(holder-or-param, anchor-or-None) for one layer call."""
+    return param if (param is None or _grad_target(param) is None) else _P(param)
+
+
+def _anchor(x, *params):
+    if any(p is not None and _grad_target(p) is not None for p in params) and torch.is_grad_enabled():
+        return torch.empty(0, device=x.device, dtype=torch.float32, requires_grad=True)
+    return None
+
+
 def _grad_target(p: Optional[torch.Tensor]):
     """fp32 gradient buffer to accumulate into (arena view) or None."""
     if p is None or p.grad is None or p.grad.dtype != torch.float32:
@@ -53,7 +81,8 @@ def _shadow(module: nn.Module, name: str, param: torch.Tensor, as2d: bool = True
 # ================================================================================ Linear
 class _LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, w_bf16, act, out_fp32, flags_cfg):
+    def forward(ctx, x, weight, bias, w_bf16, act, out_fp32, flags_cfg, anchor):
+        weight, bias = _unwrap(weight), _unwrap(bias)
         x2 = x.reshape(-1, x.shape[-1])
         kw = {}
         if flags_cfg is not None:
@@ -103,7 +132,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_dx:
             # dgrad: dX[M, K] = dY[M, N] W[N, K]   (B = W is MN-major for this product)
             dx = F.gemm(dy2, w_bf16, b_mn=True).view(ctx.x_shape)
-        return dx, gw, gb, None, None, None, None
+        return dx, gw, gb, None, None, None, None, None
 
 
 class Linear(nn.Module):
@@ -133,14 +162,15 @@ class Linear(nn.Module):
         if x.dtype != BF16:
             x = F.cast(x.contiguous(), BF16)
         cfg, self.flags_cfg = self.flags_cfg, None  # one-shot: only the first GEMM after a round is gated
-        return _LinearFn.apply(x, self.weight, self.bias, _shadow(self, "weight", self.weight), self.act,
-                               self.out_fp32, cfg)
+        return _LinearFn.apply(x, _wrap(self.weight, x), _wrap(self.bias, x), _shadow(self, "weight", self.weight),
+                               self.act, self.out_fp32, cfg, _anchor(x, self.weight))
 
 
 # ================================================================================ Conv2d (NHWC, implicit GEMM)
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, w_bf16, kh, kw, stride, pad):
+    def forward(ctx, x, weight, w_bf16, kh, kw, stride, pad, anchor):
+        weight = _unwrap(weight)
         n, h, w, c = x.shape
         cout = w_bf16.shape[0]
         if kh == 1 and kw == 1 and stride == 1 and pad == 0 and c % 8 == 0:
@@ -181,7 +211,7 @@ class _ConvFn(torch.autograd.Function):
                 dx = dcol.view(n, h, w, c)
             else:
                 dx = F.col2im(dcol, (n, h, w, c), kh, kw, stride, pad, ho, wo)
-        return dx, gw, None, None, None, None, None
+        return dx, gw, None, None, None, None, None, None
 
 
 class Conv2d(nn.Module):
@@ -210,14 +240,15 @@ class Conv2d(nn.Module):
         if not x.is_cuda:
             y = TF.conv2d(x.permute(0, 3, 1, 2), self.weight.to(x.dtype), None, self.stride, self.padding)
             return y.permute(0, 2, 3, 1)
-        return _ConvFn.apply(x, self.weight, self._w_bf16(), self.kernel_size, self.kernel_size, self.stride,
-                             self.padding)
+        return _ConvFn.apply(x, _wrap(self.weight, x), self._w_bf16(), self.kernel_size, self.kernel_size,
+                             self.stride, self.padding, _anchor(x, self.weight))
 
 
 # ================================================================================ BatchNorm (+residual +ReLU)
 class _BNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, rmean, rvar, nbt, eps, momentum, relu, training, ws):
+    def forward(ctx, x, residual, gamma, beta, rmean, rvar, nbt, eps, momentum, relu, training, ws, anchor):
+        gamma, beta = _unwrap(gamma), _unwrap(beta)
         C_ = load()
         c = x.shape[-1]
         rows = x.numel() // c
@@ -255,7 +286,7 @@ class _BNFn(torch.autograd.Function):
         C_.bn_bwd_apply(x, y, dy, dx, dres, gamma, mean, rstd, ctx.sums_b, tg, tb, ctx.rows, ctx.c, ctx.relu)
         if ctx.has_res and dres is None:
             dres = dy
-        return dx, dres, gg, gb, None, None, None, None, None, None, None, None
+        return dx, dres, gg, gb, None, None, None, None, None, None, None, None, None
 
 
 class BatchNorm2d(nn.Module):
@@ -285,9 +316,9 @@ class BatchNorm2d(nn.Module):
         ws = self.workspace
         if ws is None:
             ws = torch.zeros(4 * self.num_features, dtype=torch.float32, device=x.device)
-        return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
-                           self.num_batches_tracked if self.training else None, self.eps, self.momentum, self.relu,
-                           self.training, ws)
+        return _BNFn.apply(x, residual, _wrap(self.weight, x), _wrap(self.bias, x), self.running_mean,
+                           self.running_var, self.num_batches_tracked if self.training else None, self.eps,
+                           self.momentum, self.relu, self.training, ws, _anchor(x, self.weight))
 
 
 # ================================================================================ pooling / misc
@@ -342,7 +373,8 @@ class GlobalAvgPool(nn.Module):
 # ================================================================================ LayerNorm / GELU / softmax
 class _LNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, eps):
+    def forward(ctx, x, residual, gamma, beta, eps, anchor):
+        gamma, beta = _unwrap(gamma), _unwrap(beta)
         C_ = load()
         c = x.shape[-1]
         rows = x.numel() // c
@@ -368,7 +400,7 @@ class _LNFn(torch.autograd.Function):
         if tb is None:
             gb = tb = torch.zeros(ctx.c, dtype=torch.float32, device=dy.device)
         C_.layernorm_bwd(pre, dy, dx, ctx.gamma, mean, rstd, tg, tb, ctx.rows, ctx.c)
-        return dx, (dx if ctx.has_res else None), gg, gb, None
+        return dx, (dx if ctx.has_res else None), gg, gb, None, None
 
 
 class LayerNorm(nn.Module):
@@ -385,8 +417,8 @@ class LayerNorm(nn.Module):
             if residual is not None:
                 x = x + residual
             return TF.layer_norm(x, (self.c,), self.weight.to(x.dtype), self.bias.to(x.dtype), self.eps)
-        return _LNFn.apply(x.contiguous(), None if residual is None else residual.contiguous(), self.weight,
-                           self.bias, self.eps)
+        return _LNFn.apply(x.contiguous(), None if residual is None else residual.contiguous(),
+                           _wrap(self.weight, x), _wrap(self.bias, x), self.eps, _anchor(x, self.weight))
 
 
 class _SoftmaxFn(torch.autograd.Function):
@@ -524,7 +556,8 @@ def attention(qkv: torch.Tensor, B: int, S: int, H: int, dh: int) -> torch.Tenso
 
 class _EmbedFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, table, table_bf16, ids):
+    def forward(ctx, table, table_bf16, ids, anchor):
+        table = _unwrap(table)
         ctx.save_for_backward(ids)
         ctx.table = table
         return F.gather_rows(table_bf16, ids)
@@ -538,7 +571,7 @@ class _EmbedFn(torch.autograd.Function):
         if tgt is None:
             g = tgt = torch.zeros_like(table, dtype=torch.float32)
         F.embedding_bwd_(dy.contiguous(), ids, tgt)
-        return g, None, None
+        return g, None, None, None
 
 
 class Embedding(nn.Module):
@@ -552,4 +585,5 @@ class Embedding(nn.Module):
         flat = ids.reshape(-1)
         if not ids.is_cuda:
             return TF.embedding(flat, self.weight)
-        return _EmbedFn.apply(self.weight, _shadow(self, "weight", self.weight), flat)
+        return _EmbedFn.apply(_wrap(self.weight, flat), _shadow(self, "weight", self.weight), flat,
+                              _anchor(flat, self.weight))

@@ -79,7 +79,11 @@ async def test_seated_plane_round_trip_and_pull_global(tmp_path):
             for k, v in w.model.state_dict().items():
                 assert torch.allclose(v, want[k], atol=1e-6)
         # the manager's copy is stale until asked; /state_dict (and the checkpoint) pull it from seat 0
-        assert exp.model_is_stale is False or exp.last_checkpoint          # checkpoint already pulled it
+        for _ in range(500):            # the checkpoint is written right after the round lock is released
+            if exp.last_checkpoint:
+                break
+            await asyncio.sleep(0.01)
+        assert exp.last_checkpoint and exp.model_is_stale is False          # the checkpoint pulled it
         async with fed.client.get("/lineartest/state_dict") as r:
             sd = wire.loads(await r.read())["state_dict"]
         for k in want:
