@@ -60,6 +60,33 @@ void gemm_batched(const at::Tensor& a, const at::Tensor& b, at::Tensor d, int64_
         "gemm_bf16_batched");
 }
 
+void gemm_fp8(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::optional<at::Tensor>& bias,
+              const std::optional<at::Tensor>& sfa, const std::optional<at::Tensor>& sfb, int64_t M, int64_t N, int64_t K,
+              int64_t lda, int64_t ldb, int64_t ldd, int64_t act, int64_t split_k, bool accumulate, double alpha) {
+  CHECK_CUDA(a); CHECK_CUDA(b); CHECK_CUDA(d);
+  TORCH_CHECK(a.element_size() == 1 && b.element_size() == 1, "gemm_fp8 operands must be 1-byte (e4m3)");
+  const c10::cuda::CUDAGuard guard(a.device());
+  check(b200_gemm_fp8(cptr(a), cptr(b), ptr(d), opt_ptr<const float>(bias), opt_ptr<const void>(sfa),
+                      opt_ptr<const void>(sfb), M, N, K, lda, ldb, ldd, d.scalar_type() == at::kFloat, act, split_k,
+                      accumulate, static_cast<float>(alpha), cur_stream()),
+        "gemm_fp8");
+}
+void quant_mx_rows(const at::Tensor& x, at::Tensor q, at::Tensor sf, int64_t R, int64_t C, int64_t ld_in, int64_t Cp) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_quant_mx_rows(x.data_ptr(), q.data_ptr(), sf.data_ptr(), R, C, ld_in, Cp, cur_stream()), "quant_mx_rows");
+}
+void quant_mx_cols(const at::Tensor& x, at::Tensor q, at::Tensor sf, int64_t R, int64_t C, int64_t ld_in, int64_t Rp) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  check(b200_quant_mx_cols(x.data_ptr(), q.data_ptr(), sf.data_ptr(), R, C, ld_in, Rp, cur_stream()), "quant_mx_cols");
+}
+void dequant_mx(const at::Tensor& q, const at::Tensor& sf, at::Tensor out, int64_t R, int64_t C, int64_t Cp) {
+  CHECK_CUDA(q);
+  const c10::cuda::CUDAGuard guard(q.device());
+  check(b200_dequant_mx(q.data_ptr(), sf.data_ptr(), out.data_ptr<float>(), R, C, Cp, cur_stream()), "dequant_mx");
+}
+
 void fused_sgd(at::Tensor w, at::Tensor g, const std::optional<at::Tensor>& mom, const std::optional<at::Tensor>& wb,
                const at::Tensor& hyper, bool zero_grad, bool nesterov) {
   CHECK_CUDA(w);
@@ -369,6 +396,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("MAX_RANKS") = B200_MAX_RANKS;
   m.def("gemm", &gemm);
   m.def("gemm_batched", &gemm_batched);
+  m.def("gemm_fp8", &gemm_fp8);
+  m.def("quant_mx_rows", &quant_mx_rows);
+  m.def("quant_mx_cols", &quant_mx_cols);
+  m.def("dequant_mx", &dequant_mx);
   m.def("fused_sgd", &fused_sgd);
   m.def("weighted_sum", &weighted_sum);
   m.def("cast", &cast);

@@ -18,6 +18,14 @@ int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int M, int N, 
                            long long ldd, int a_mn, int b_mn, int out_fp32, int act, float alpha, int n_outer,
                            int n_inner, long long a_outer, long long a_inner, long long b_outer, long long b_inner,
                            long long d_outer, long long d_inner, int accumulate, cudaStream_t stream);
+// ---- gemm_fp8.cu / quant.cu (MXFP8: e4m3 + UE8M0 scale per 32 elements of K)
+int b200_gemm_fp8(const void* a, const void* b, void* d, const float* bias, const void* sfa, const void* sfb, int M, int N,
+                  int K, long long lda, long long ldb, long long ldd, int out_fp32, int act, int split_k, int accumulate,
+                  float alpha, cudaStream_t stream);
+int b200_quant_mx_rows(const void* x, void* q, void* sf, long long R, int C, long long ld_in, int Cp, cudaStream_t stream);
+int b200_quant_mx_cols(const void* x, void* q, void* sf, long long R, int C, long long ld_in, long long Rp,
+                       cudaStream_t stream);
+int b200_dequant_mx(const void* q, const void* sf, float* out, long long R, int C, int Cp, cudaStream_t stream);
 int b200_gemm_simt(const void* a, const void* b, void* d, const float* bias, int M, int N, int K, long long lda,
                    long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act, int accumulate,
                    float alpha, cudaStream_t stream);

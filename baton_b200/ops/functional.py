@@ -274,3 +274,51 @@ def gemm_batched(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int,
 
 def embedding_bwd_(dy2d: torch.Tensor, idx: torch.Tensor, grad_table: torch.Tensor) -> None:
     load().embedding_bwd(dy2d, idx, grad_table)
+
+
+# ---------------------------------------------------------------------------- MXFP8 (block-scaled fp8)
+def _sf_bytes(rows: int, k: int) -> int:
+    return ((rows + 127) // 128) * ((k + 127) // 128) * 512
+
+
+def quant_mx_rows(x2d: torch.Tensor):
+    """bf16 ``[R, C]`` -> (e4m3 ``[R, Cp]`` as uint8, UE8M0 scale atoms); scales along C."""
+    R, C = x2d.shape
+    Cp = round_up(C, 16)
+    q = torch.empty((R, Cp), dtype=torch.uint8, device=x2d.device)
+    sf = torch.empty(_sf_bytes(R, C), dtype=torch.uint8, device=x2d.device)
+    load().quant_mx_rows(x2d, q, sf, R, C, x2d.stride(0), Cp)
+    return q, sf
+
+
+def quant_mx_cols(x2d: torch.Tensor):
+    """bf16 ``[R, C]`` -> (e4m3 ``[C, Rp]`` = quantised TRANSPOSE, scale atoms); scales along R."""
+    R, C = x2d.shape
+    Rp = round_up(R, 16)
+    q = torch.zeros((C, Rp), dtype=torch.uint8, device=x2d.device) if Rp != R else \
+        torch.empty((C, Rp), dtype=torch.uint8, device=x2d.device)
+    sf = torch.empty(_sf_bytes(C, R), dtype=torch.uint8, device=x2d.device)
+    load().quant_mx_cols(x2d, q, sf, R, C, x2d.stride(0), Rp)
+    return q, sf
+
+
+def dequant_mx(q: torch.Tensor, sf: torch.Tensor, cols: int) -> torch.Tensor:
+    R, Cp = q.shape
+    out = torch.empty((R, cols), dtype=torch.float32, device=q.device)
+    load().dequant_mx(q, sf, out, R, cols, Cp)
+    return out
+
+
+def gemm_fp8(qa: torch.Tensor, sfa, qb: torch.Tensor, sfb, K: int, *, out: Optional[torch.Tensor] = None,
+             out_dtype: torch.dtype = BF16, bias: Optional[torch.Tensor] = None, act: int = 0,
+             accumulate: bool = False, alpha: float = 1.0, split_k: int = 1, n_valid: Optional[int] = None):
+    """``out[M,N] = act(alpha * (A*SFA) @ (B*SFB)^T + bias)`` with e4m3 operands ``qa [M,Kp]``, ``qb [N,Kp]``."""
+    M, N = qa.shape[0], qb.shape[0]
+    if n_valid is not None:
+        N = min(N, n_valid)
+    if out is None:
+        out = torch.zeros((M, N), dtype=out_dtype, device=qa.device) if accumulate else \
+            torch.empty((M, N), dtype=out_dtype, device=qa.device)
+    ldd = out.stride(0) if out.dim() == 2 else N
+    load().gemm_fp8(qa, qb, out, bias, sfa, sfb, M, N, K, qa.stride(0), qb.stride(0), ldd, act, split_k, accumulate, alpha)
+    return out
