@@ -104,6 +104,16 @@ class ResNet(FederatedModule):
             layers.append(block(self.inplanes, planes))
         return nn.Sequential(*layers)
 
+    def set_precision(self, dtype: str = "bf16") -> "ResNet":
+        """``"fp8"``: every convolution (forward, dgrad and wgrad GEMMs) runs on the block-scaled
+        MXFP8 tensor-core path; BatchNorm, the classifier head and the optimizer stay bf16/fp32."""
+        assert dtype in ("bf16", "fp8")
+        for m in self.modules():
+            if isinstance(m, bnn.Conv2d):
+                m.fp8 = dtype == "fp8"
+        self.compute_dtype = dtype
+        return self
+
     def forward(self, x):
         """``x``: NHWC ``[N, H, W, C]`` (bf16 on CUDA)."""
         x = self.maxpool(self.bn1(self.conv1(x)))

@@ -161,6 +161,9 @@ class Linear(nn.Module):
             return TF.relu(y) if self.act == 1 else (TF.gelu(y, approximate="tanh") if self.act == 2 else y)
         if x.dtype != BF16:
             x = F.cast(x.contiguous(), BF16)
+        if getattr(self, "fp8", False) and self.act == 0 and self.bias is None and not self.out_fp32:
+            y = matmul_fp8(x.reshape(-1, x.shape[-1]), self, _shadow(self, "weight", self.weight), self.in_features)
+            return y.view(*x.shape[:-1], self.out_features)
         cfg, self.flags_cfg = self.flags_cfg, None  # one-shot: only the first GEMM after a round is gated
         return _LinearFn.apply(x, _wrap(self.weight, x), _wrap(self.bias, x), _shadow(self, "weight", self.weight),
                                self.act, self.out_fp32, cfg, _anchor(x, self.weight))
@@ -240,6 +243,8 @@ class Conv2d(nn.Module):
         if not x.is_cuda:
             y = TF.conv2d(x.permute(0, 3, 1, 2), self.weight.to(x.dtype), None, self.stride, self.padding)
             return y.permute(0, 2, 3, 1)
+        if getattr(self, "fp8", False):
+            return conv2d_fp8(x, self)
         return _ConvFn.apply(x, _wrap(self.weight, x), self._w_bf16(), self.kernel_size, self.kernel_size,
                              self.stride, self.padding, _anchor(x, self.weight))
 
@@ -587,3 +592,86 @@ class Embedding(nn.Module):
             return TF.embedding(flat, self.weight)
         return _EmbedFn.apply(_wrap(self.weight, flat), _shadow(self, "weight", self.weight), flat,
                               _anchor(flat, self.weight))
+
+
+# ================================================================================ MXFP8 matmul (block-scaled fp8 training)
+class _MatmulFp8Fn(torch.autograd.Function):
+    """``y = x w^T`` with every GEMM of the layer -- forward, dgrad, wgrad -- on the block-scaled
+    fp8 tensor-core path.  Each operand is quantised (e4m3 + UE8M0 scale per 32 elements) along the
+    reduction dimension of the GEMM that consumes it; the transposed operands of dgrad / wgrad come
+    out of the fused quantise+transpose kernel, so the GEMM kernel only ever sees K-major inputs.
+    The weight gradient is accumulated in fp32 straight into the gradient arena."""
+
+    @staticmethod
+    def forward(ctx, x2, weight, w_bf16, k_true, anchor):
+        weight = _unwrap(weight)
+        K = x2.shape[1]
+        xq, sx = F.quant_mx_rows(x2)
+        wq, sw = F.quant_mx_rows(w_bf16)
+        y = F.gemm_fp8(xq, sx, wq, sw, K)
+        ctx.save_for_backward(x2, w_bf16)
+        ctx.weight, ctx.k_true = weight, k_true
+        ctx.needs_dx = x2.requires_grad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w_bf16 = ctx.saved_tensors
+        dy = dy.contiguous()
+        M, N = dy.shape
+        K = x2.shape[1]
+        weight, k_true = ctx.weight, ctx.k_true
+        # wgrad: dW[N, K] = dY^T[N, M] X^T[K, M]^T   (reduction over M)
+        dyt, sdyt = F.quant_mx_cols(dy)
+        xt, sxt = F.quant_mx_cols(x2)
+        gw = None
+        tgt = _grad_target(weight)
+        if tgt is not None:
+            out2d = tgt.permute(0, 2, 3, 1).reshape(N, k_true) if tgt.dim() == 4 else tgt.view(N, k_true)
+            F.gemm_fp8(dyt, sdyt, xt, sxt, M, out=out2d, accumulate=True, n_valid=k_true)
+        else:
+            g2 = F.gemm_fp8(dyt, sdyt, xt, sxt, M, out_dtype=torch.float32, accumulate=True, n_valid=k_true)
+            gw = g2.view(weight.shape[0], *weight.shape[2:], weight.shape[1]).permute(0, 3, 1, 2) if weight.dim() == 4 \
+                else g2.view_as(weight)
+        dx = None
+        if ctx.needs_dx:
+            # dgrad: dX[M, K] = dY[M, N] (W^T)[K, N]^T   (reduction over N)
+            dyq, sdy = F.quant_mx_rows(dy)
+            wt, swt = F.quant_mx_cols(w_bf16)
+            dx = F.gemm_fp8(dyq, sdy, wt, swt, N)
+        return dx, gw, None, None, None
+
+
+def matmul_fp8(x2: torch.Tensor, module: nn.Module, w_bf16: torch.Tensor, k_true: int) -> torch.Tensor:
+    return _MatmulFp8Fn.apply(x2, _wrap(module.weight, x2), w_bf16, k_true, _anchor(x2, module.weight))
+
+
+class _Im2colFn(torch.autograd.Function):
+    """im2col as its own differentiable op (its adjoint is col2im) so the fp8 matmul above can sit
+    between it and the BatchNorm that follows."""
+
+    @staticmethod
+    def forward(ctx, x, kh, kw, stride, pad):
+        col, ho, wo, kp = F.im2col(x, kh, kw, stride, pad)
+        ctx.geom = (tuple(x.shape), kh, kw, stride, pad, ho, wo)
+        return col
+
+    @staticmethod
+    def backward(ctx, dcol):
+        shape, kh, kw, stride, pad, ho, wo = ctx.geom
+        return F.col2im(dcol.contiguous(), shape, kh, kw, stride, pad, ho, wo), None, None, None, None
+
+
+def conv2d_fp8(x: torch.Tensor, conv: "Conv2d") -> torch.Tensor:
+    """NHWC convolution with all three GEMMs in MXFP8."""
+    n, h, w, c = x.shape
+    k, s, p = conv.kernel_size, conv.stride, conv.padding
+    ho, wo = F.conv_out_size(h, k, s, p), F.conv_out_size(w, k, s, p)
+    if k == 1 and s == 1 and p == 0 and c % 16 == 0:
+        col = x.reshape(n * h * w, c)
+    elif c % 8 == 0:
+        col = _Im2colFn.apply(x, k, k, s, p)
+    else:   # stem (C = 3): no input gradient needed, plain im2col
+        col = F.im2col(x, k, k, s, p)[0]
+    y = matmul_fp8(col, conv, conv._w_bf16(), conv.k_true)
+    return y.view(n, ho, wo, conv.out_channels)

@@ -42,6 +42,8 @@ def parse_args(argv=None):
     ap.add_argument("--momentum", type=float, default=0.0)
     ap.add_argument("--alpha", type=float, default=0.5, help="Dirichlet label skew of the shards")
     ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"],
+                    help="fp8 = block-scaled MXFP8 convolutions (fwd/dgrad/wgrad), everything else bf16/fp32")
     ap.add_argument("--backend", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--n-ctas", type=int, default=296)
     ap.add_argument("--no-graph", action="store_true")
@@ -134,6 +136,8 @@ def main(argv=None):
         model = resnet50(1000 if args.samples >= 1000 else 10)
     else:
         raise SystemExit("bench supports resnet18/resnet50")
+    if args.dtype == "fp8":
+        model.set_precision("fp8")
     eng = FederatedEngine(model, dev, backend=args.backend, lr=args.lr, batch_size=args.batch_size,
                           momentum=args.momentum, wire_dtype=args.wire, n_ctas=args.n_ctas,
                           use_graph=not args.no_graph, nvls=(args.nvls if args.nvls == "auto" else args.nvls == "1"),
@@ -240,7 +244,8 @@ def main(argv=None):
             "metric": "federated local samples/sec (whole box), ResNet-18 FedAvg, synthetic non-IID 32x32 shards",
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "rounds_per_s": args.steps / (dev_ms / 1e3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.dtype == "bf16" else "mxfp8 convs (e4m3 + ue8m0/32) + bf16", "data": "synthetic",
             "config": {"model": "{}(num_classes={})".format(args.model, num_classes),
                        "global_batch": world * args.batch_size, "batch_size": args.batch_size,
                        "samples_per_client": args.samples, "image": "32x32x3 NHWC", "seq_len": None,

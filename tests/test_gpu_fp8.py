@@ -69,3 +69,50 @@ def test_gemm_fp8_unscaled_kind():
     ref = qa.float() @ qb.float().t()
     out = F.gemm_fp8(qa.view(torch.uint8), None, qb.view(torch.uint8), None, K, out_dtype=torch.float32, alpha=0.5)
     assert _rel(out, 0.5 * ref) < 2e-3
+
+
+def test_conv_and_linear_layers_in_mxfp8_track_bf16():
+    from baton_b200.ops import nn as bnn
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    cos = torch.nn.functional.cosine_similarity
+    for (cin, k, stride, pad, h) in [(64, 3, 1, 1, 8), (128, 1, 1, 0, 4), (64, 3, 2, 1, 8)]:
+        conv = bnn.Conv2d(cin, 128, k, stride, pad).to(dev)
+        x = torch.randn(16, h, h, cin, device=dev).to(BF16)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        y_ref = conv(xa)
+        dy = torch.randn_like(y_ref)
+        y_ref.backward(dy)
+        g_ref, conv.weight.grad = conv.weight.grad.clone(), None
+        conv.fp8 = True
+        y = conv(xb)
+        y.backward(dy)
+        assert float(cos(y.float().flatten(), y_ref.float().flatten(), dim=0)) > 0.995
+        assert float(cos(xb.grad.float().flatten(), xa.grad.float().flatten(), dim=0)) > 0.99
+        assert float(cos(conv.weight.grad.flatten(), g_ref.flatten(), dim=0)) > 0.99
+    lin = bnn.Linear(512, 256, bias=False).to(dev)
+    x = torch.randn(300, 512, device=dev).to(BF16)
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    y_ref = lin(xa); dy = torch.randn_like(y_ref); y_ref.backward(dy)
+    g_ref, lin.weight.grad = lin.weight.grad.clone(), None
+    lin.fp8 = True
+    y = lin(xb); y.backward(dy)
+    assert float(cos(y.float().flatten(), y_ref.float().flatten(), dim=0)) > 0.995
+    assert float(cos(lin.weight.grad.flatten(), g_ref.flatten(), dim=0)) > 0.99
+
+
+def test_resnet18_trains_in_mxfp8_under_cuda_graph():
+    from baton_b200.data import ShardSpec, image_shard
+    from baton_b200.models import resnet18
+    from baton_b200.parallel.arena import ParamArena
+    from baton_b200.train import GraphedLocalSGD
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    X, y = image_shard(ShardSpec(0, torch.full((10,), 0.1), 512), noise=0.3)
+    X, y = X.to(dev).to(BF16), y.to(dev)
+    m = resnet18(10).set_precision("fp8")
+    arena = ParamArena(m, dev, momentum=True)
+    m.build_workspace(dev)
+    m._graphed_trainer = GraphedLocalSGD(m, arena, loss="ce")
+    hist = m.train(X, y, n_epoch=6, lr=0.05, batch_size=128, momentum=0.9)
+    assert hist[-1] < hist[0] * 0.8, hist
