@@ -34,6 +34,9 @@ def main() -> int:
     ap.add_argument("--wire", default="bf16")
     args, _ = ap.parse_known_args()
 
+    sys.stdout.flush()
+    real_stdout = os.dup(1)      # keep stdout for the single JSON line; NCCL banners etc. go to stderr
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import torchvision
@@ -152,7 +155,7 @@ def main() -> int:
     dev_ms, e2e_ms, agg_us = [float(x) for x in t.tolist()]
     if rank == 0:
         per_round = world * args.samples * args.local_epochs
-        print(json.dumps({
+        os.write(real_stdout, (json.dumps({
             "impl": "baseline",
             "metric": "federated local samples/sec (whole box), ResNet-18 FedAvg, synthetic non-IID 32x32 shards",
             "value": per_round * args.steps / (dev_ms / 1e3), "unit": "samples/s", "n_gpus": world,
@@ -168,7 +171,7 @@ def main() -> int:
                     "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4 * args.local_epochs},
             "agg_bcast_us_per_round": agg_us, "final_loss": last[-1] if last else None,
-        }))
+        }) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -32,9 +32,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.path.join(HERE, "_ref")
 
 
+_REAL_FD = None
+
+
 def _unavailable(why: str) -> None:
     if int(os.environ.get("RANK", "0")) == 0:
-        print(json.dumps({"impl": "reference", "unavailable": why}), file=sys.__stdout__, flush=True)
+        os.write(_REAL_FD if _REAL_FD is not None else 1, (json.dumps({"impl": "reference", "unavailable": why}) + "\n").encode())
     sys.exit(0)
 
 
@@ -51,7 +54,11 @@ def main() -> None:
     ap.add_argument("--role", default="bench", choices=["bench", "manager"])
     args, _ = ap.parse_known_args()
     # the reference logs with print(); keep stdout clean for the single JSON result line
-    real_stdout = sys.stdout
+    sys.stdout.flush()
+    global _REAL_FD
+    _REAL_FD = os.dup(1)
+    real_stdout = os.fdopen(os.dup(_REAL_FD), "w")
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
 
     if not os.path.exists(os.path.join(REF, "manager.py")):

@@ -101,6 +101,19 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _claim_stdout():
+    """Everything written to fd 1 from here on (NCCL's version banner, library chatter) goes to stderr;
+    the returned fd is the real stdout, used once for the single JSON result line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_fd: int, obj) -> None:
+    os.write(real_fd, (json.dumps(obj) + "\n").encode())
+
+
 def main(argv=None):
     args = parse_args(argv)
     if args.impl == "reference":
@@ -108,6 +121,7 @@ def main(argv=None):
     if args.impl == "baseline":
         os.execv(sys.executable, [sys.executable, os.path.join(ROOT, "baseline", "nccl_fedavg.py")] + sys.argv[1:])
 
+    real_stdout = _claim_stdout()
     import torch
     import torch.distributed as dist
 
@@ -116,7 +130,7 @@ def main(argv=None):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         if rank == 0:
-            print(json.dumps({"metric": "federated local samples/sec", "value": None, "error": "no CUDA device"}))
+            _emit(real_stdout, {"metric": "federated local samples/sec", "value": None, "error": "no CUDA device"})
         return 1
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
@@ -267,7 +281,7 @@ def main(argv=None):
             "final_loss": (res.loss_history[-1] if res and res.loss_history else None),
             "launch_breakdown": dict(launch_counts()),
         }
-        print(json.dumps(out))
+        _emit(real_stdout, out)
     if world > 1:
         dist.destroy_process_group()
     return 0
