@@ -182,7 +182,8 @@ def test_weighted_sum_cast_gather_colsum(F):
 
 
 # ------------------------------------------------------------------ conv plumbing
-@pytest.mark.parametrize("cin,k,stride,pad,h", [(64, 3, 1, 1, 8), (64, 3, 2, 1, 8), (3, 7, 2, 3, 32), (64, 1, 2, 0, 8)])
+@pytest.mark.parametrize("cin,k,stride,pad,h", [(64, 3, 1, 1, 8), (64, 3, 2, 1, 8), (3, 7, 2, 3, 32), (64, 1, 2, 0, 8),
+                                                (512, 3, 1, 1, 1), (256, 3, 2, 1, 1)])
 def test_conv2d_forward_backward_vs_torch(bnn, cin, k, stride, pad, h):
     torch.manual_seed(5)
     dev = _dev()
