@@ -18,8 +18,11 @@ namespace b200 {
 
 __device__ __forceinline__ int mx_exponent(float amax) {
   // shared exponent = floor(log2(amax)) - emax(e4m3 = 8), clamped to the UE8M0 range
+  // (bumped by one when amax / 2^e would exceed 448 = max e4m3, so the block maximum never saturates)
   if (!(amax > 0.f)) return -127;
-  const int e = static_cast<int>((__float_as_uint(amax) >> 23) & 0xFF) - 127 - 8;
+  const uint32_t bits = __float_as_uint(amax);
+  int e = static_cast<int>((bits >> 23) & 0xFF) - 127 - 8;
+  if ((bits & 0x7FFFFFu) > 0x600000u) e += 1;   // mantissa > 1.75  <=>  amax * 2^-e > 448
   return e < -127 ? -127 : (e > 127 ? 127 : e);
 }
 __device__ __forceinline__ float exp2_int(int e) {   // 2^e for e in [-127, 127]
