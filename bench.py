@@ -34,7 +34,8 @@ def parse_args(argv=None):
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "baseline"])
-    ap.add_argument("--model", default="resnet18")
+    ap.add_argument("--model", default="resnet18", choices=["resnet18", "resnet50", "bert_base", "bert_tiny"])
+    ap.add_argument("--seq-len", type=int, default=128)
     ap.add_argument("--batch-size", type=int, default=128)
     ap.add_argument("--samples", type=int, default=4096, help="samples per client per round")
     ap.add_argument("--local-epochs", type=int, default=1)
@@ -138,8 +139,8 @@ def main(argv=None):
         dist.init_process_group("nccl", device_id=dev)
 
     sys.path.insert(0, ROOT)
-    from baton_b200.data import dirichlet_label_shards, image_shard
-    from baton_b200.models import resnet18, resnet50
+    from baton_b200.data import dirichlet_label_shards, image_shard, token_shard
+    from baton_b200.models import bert_base, bert_tiny, resnet18, resnet50
     from baton_b200.ops._ext import launch_counts, total_launches
     from baton_b200.parallel.engine import FederatedEngine
 
@@ -148,8 +149,11 @@ def main(argv=None):
         model = resnet18(10)
     elif args.model == "resnet50":
         model = resnet50(1000 if args.samples >= 1000 else 10)
+    elif args.model == "bert_base":
+        model = bert_base(2)
     else:
-        raise SystemExit("bench supports resnet18/resnet50")
+        model = bert_tiny(2)
+    is_bert = args.model.startswith("bert")
     if args.dtype == "fp8":
         model.set_precision("fp8")
     eng = FederatedEngine(model, dev, backend=args.backend, lr=args.lr, batch_size=args.batch_size,
@@ -158,11 +162,15 @@ def main(argv=None):
                           name=args.model, logical_clients=args.logical_clients, sample_k=args.sample_k, seed=5)
 
     # private synthetic non-IID shard of this client, in pinned host memory (bf16 NHWC) + resident copy
-    num_classes = model.fc.out_features
+    num_classes = model.config.num_labels if is_bert else model.fc.out_features
     n_logical = args.logical_clients if args.logical_clients > world else world
     specs = dirichlet_label_shards(n_logical, num_classes, args.samples, alpha=args.alpha, seed=11)
     mine = [c for c in range(n_logical) if c % world == rank]
-    host_shards = {c: image_shard(specs[c], seed=3, dtype=torch.bfloat16, pin=True) for c in mine}
+    if is_bert:
+        host_shards = {c: token_shard(specs[c], seq_len=args.seq_len, vocab=model.config.vocab_size, seed=3, pin=True)
+                       for c in mine}
+    else:
+        host_shards = {c: image_shard(specs[c], seed=3, dtype=torch.bfloat16, pin=True) for c in mine}
     dev_shards = {c: (x.to(dev), y.to(dev)) for c, (x, y) in host_shards.items()}
     X_host, y_host = host_shards[mine[0]]
     X_dev, y_dev = dev_shards[mine[0]]
@@ -255,14 +263,17 @@ def main(argv=None):
         e2e_value = float(cnt[1]) * args.local_epochs / (e2e_ms / 1e3)
         wire_bytes = eng.session.wire_bytes()
         out = {
-            "metric": "federated local samples/sec (whole box), ResNet-18 FedAvg, synthetic non-IID 32x32 shards",
+            "metric": "federated local samples/sec (whole box), {} FedAvg, synthetic non-IID {} shards".format(
+                {"resnet18": "ResNet-18", "resnet50": "ResNet-50", "bert_base": "BERT-base", "bert_tiny": "BERT-tiny"}[args.model],
+                "seq-{} token".format(args.seq_len) if is_bert else "32x32"),
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms / args.steps, "rounds_per_s": args.steps / (dev_ms / 1e3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.dtype == "bf16" else "mxfp8 convs (e4m3 + ue8m0/32) + bf16", "data": "synthetic",
             "config": {"model": "{}(num_classes={})".format(args.model, num_classes),
                        "global_batch": world * args.batch_size, "batch_size": args.batch_size,
-                       "samples_per_client": args.samples, "image": "32x32x3 NHWC", "seq_len": None,
+                       "samples_per_client": args.samples, "image": None if is_bert else "32x32x3 NHWC",
+                       "seq_len": args.seq_len if is_bert else None,
                        "local_epochs": args.local_epochs, "parallelism": "fedavg dp{}".format(world),
                        "backend": args.backend, "wire_dtype": args.wire, "upload": "delta",
                        "nvls": bool(getattr(eng.session, "use_nvls", False)),
