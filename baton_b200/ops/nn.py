@@ -59,6 +59,54 @@ def _anchor(x, *params):
     return None
 
 
+class _WgradOverlap:
+    """Weight-gradient GEMMs only feed the optimizer, so they are forked onto a side stream and overlap
+    the dgrad -> BatchNorm-backward chain of the layers below (inside a captured graph this becomes a
+    parallel branch).  Operand tensors are kept alive until the join so the caching allocator cannot hand
+    their memory to the main stream early; the join is queued as an autograd end-of-backward callback and
+    is also called by the trainer before the optimizer step."""
+
+    def __init__(self):
+        import os
+        self.enabled = os.environ.get("BATON_WGRAD_OVERLAP", "1") != "0"
+        self.streams = {}
+        self.keep = []
+        self.pending = False
+        self.queued = False
+
+    def run(self, fn, *keep):
+        if not self.enabled or not keep[0].is_cuda:
+            return fn()
+        dev = keep[0].device
+        side = self.streams.get(dev)
+        if side is None:
+            side = self.streams[dev] = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            fn()
+        self.keep.append(keep)
+        self.pending = True
+        if not self.queued:
+            self.queued = True
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(self.join)
+            except Exception:      # not inside a backward pass
+                self.queued = False
+
+    def join(self):
+        self.queued = False
+        if not self.pending:
+            return
+        for dev, side in self.streams.items():
+            torch.cuda.current_stream(dev).wait_stream(side)
+        self.keep.clear()
+        self.pending = False
+
+
+WGRAD = _WgradOverlap()
+
+
 def _grad_target(p: Optional[torch.Tensor]):
     """fp32 gradient buffer to accumulate into (arena view) or None."""
     if p is None or p.grad is None or p.grad.dtype != torch.float32:
@@ -119,7 +167,8 @@ class _LinearFn(torch.autograd.Function):
         # wgrad: dW[N, K] += dY^T[N, M] X[M, K]   (both operands MN-major, no transposes)
         tgt = _grad_target(weight)
         if tgt is not None:
-            F.gemm(dy2, x2, a_mn=True, b_mn=True, out=tgt.view(weight.shape[0], -1), accumulate=True)
+            out2d = tgt.view(weight.shape[0], -1)
+            WGRAD.run(lambda: F.gemm(dy2, x2, a_mn=True, b_mn=True, out=out2d, accumulate=True), dy2, x2)
         else:
             gw = F.gemm(dy2, x2, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True).view_as(weight)
         if bias is not None:
@@ -219,7 +268,10 @@ class _ConvFn(torch.autograd.Function):
                 full = tgt.permute(0, 2, 3, 1).reshape(cout, kh * kw, c)
                 assert full.data_ptr() == tgt.data_ptr(), "conv weight grad must be channels_last in the arena"
                 g2d = full[:, tap, :]
-            F.gemm(dy2, col, a_mn=True, b_mn=True, out=g2d, accumulate=True)
+            if tgt is None:
+                F.gemm(dy2, col, a_mn=True, b_mn=True, out=g2d, accumulate=True)
+            else:
+                WGRAD.run(lambda: F.gemm(dy2, col, a_mn=True, b_mn=True, out=g2d, accumulate=True), dy2, col)
             dx = None
             if ctx.needs_dx:
                 wc = w_bf16.view(cout, kh * kw, c)[:, tap, :]
@@ -229,7 +281,8 @@ class _ConvFn(torch.autograd.Function):
             # the arena view is channels_last: physical [Cout, KH, KW, Cin] == [Cout, K]
             out2d = tgt.permute(0, 2, 3, 1).reshape(cout, k_true) if tgt.dim() == 4 else tgt.view(cout, k_true)
             assert out2d.data_ptr() == tgt.data_ptr(), "conv weight grad must be channels_last in the arena"
-            F.gemm(dy2, col, a_mn=True, b_mn=True, out=out2d, accumulate=True, n_valid=k_true)
+            WGRAD.run(lambda: F.gemm(dy2, col, a_mn=True, b_mn=True, out=out2d, accumulate=True, n_valid=k_true),
+                      dy2, col)
         else:
             g2 = F.gemm(dy2, col, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True, n_valid=k_true)
             gw = g2.view(cout, kh, kw, c).permute(0, 3, 1, 2)

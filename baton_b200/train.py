@@ -118,6 +118,7 @@ class GraphedLocalSGD:
         out = self.model(xb)
         loss, stats = self._loss(out, yb)
         loss.backward()
+        self.bnn.WGRAD.join()      # weight-gradient GEMMs run on a side stream; they must land before the step
         a = self.arena
         F.fused_sgd(a.theta[: a.n_param], a.grad, self.hyper, a.momentum,
                     a.theta_bf16[: a.n_param] if a.theta_bf16 is not None else None,
