@@ -57,6 +57,29 @@ class LinearTestWorker(ExperimentWorker):
         return linear_regression_shard(rng=self._rng, generator=self._gen)
 
 
+def make_gpu_worker(app, model, host: str, port: int, cfg: FederationConfig):
+    """One GPU-seated client (launch one per GPU under torchrun: RANK / LOCAL_RANK / WORLD_SIZE /
+    MASTER_* come from the environment; NCCL only bootstraps the symmetric-memory rendezvous)."""
+    import os
+
+    import torch.distributed as dist
+
+    from .control.gpu_worker import GpuExperimentWorker
+    from .data import dirichlet_label_shards, image_shard, iid_label_shards
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    specs = (dirichlet_label_shards(world, cfg.num_classes, cfg.samples_per_client, cfg.alpha, cfg.seed)
+             if cfg.partition == "dirichlet" else iid_label_shards(world, cfg.num_classes, cfg.samples_per_client))
+    X, y = image_shard(specs[rank], seed=cfg.seed, dtype=torch.bfloat16, pin=True)
+    return GpuExperimentWorker(app, model, host, device=dev, shard_fn=lambda: (X, y), backend=cfg.backend,
+                               wire_dtype=cfg.wire_dtype, momentum=cfg.momentum, port=port,
+                               heartbeat_time=cfg.heartbeat_time,
+                               train_kwargs={"lr": cfg.lr, "batch_size": cfg.batch_size})
+
+
 def make_app(role: str, host: str, port: int, cfg: Optional[FederationConfig] = None) -> web.Application:
     cfg = cfg or FederationConfig()
     app = web.Application(client_max_size=1 << 34)
@@ -64,10 +87,12 @@ def make_app(role: str, host: str, port: int, cfg: Optional[FederationConfig] = 
     if role == "manager":
         manager = Manager(app)
         manager.register_experiment(
-            model, client_ttl=cfg.client_ttl, sample_k=cfg.sample_k, seed=cfg.seed,
+            model, client_ttl=cfg.client_ttl, sample_k=cfg.sample_k, seed=cfg.seed, dataplane=cfg.backend,
             round_timeout=cfg.round_timeout, checkpoint_dir=cfg.checkpoint_dir,
             resume=bool(cfg.checkpoint_dir))
         app["manager"] = manager
+    elif role == "worker" and cfg.backend in ("fused", "nccl"):
+        app["worker"] = make_gpu_worker(app, model, host, port, cfg)
     elif role == "worker":
         worker = LinearTestWorker(
             app, model, host, port=port, heartbeat_time=cfg.heartbeat_time,

@@ -25,6 +25,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
+from ..metrics import phase
 from ..train import GraphedLocalSGD
 from .arena import ParamArena
 from .fedavg import FedAvgSession, NcclSession
@@ -67,6 +68,7 @@ class FederatedEngine:
         self._acc = None
         self.last_losses_dev = None
         self.samples_trained = 0          # samples this rank pushed through local SGD (per epoch)
+        self.phase_s: Dict[str, float] = {}   # host seconds per NVTX phase (launch cost; device time is in bench.py)
 
     # ------------------------------------------------------------------ data staging
     def stage(self, X_host: torch.Tensor, y_host: torch.Tensor, slot: int = 0):
@@ -113,8 +115,10 @@ class FederatedEngine:
             if mine:
                 X, y = shards(self.rank) if callable(shards) else shards
                 if not X.is_cuda:
-                    X, y = self.stage(X, y)
-                losses_dev = self.trainer.run(X, y, n_epoch=n_epoch, return_device=True, **self.hp)
+                    with phase("baton.h2d_shard", self.phase_s):
+                        X, y = self.stage(X, y)
+                with phase("baton.local_train", self.phase_s):
+                    losses_dev = self.trainer.run(X, y, n_epoch=n_epoch, return_device=True, **self.hp)
                 total_n = X.shape[0]
         else:
             # time-sliced logical clients: fold n_k * (theta_k - global) locally, then upload the mean
@@ -147,7 +151,8 @@ class FederatedEngine:
         if losses_dev is not None:
             steps = max(1, self.trainer.last_steps)
             loss_for_wire = losses_dev[:, 0] / steps
-        self._aggregate(float(total_n), loss_for_wire)
+        with phase("baton.aggregate_broadcast", self.phase_s):
+            self._aggregate(float(total_n), loss_for_wire)
         self.n_rounds += 1
         hist: List[float] = []
         if read_loss and losses_dev is not None:

@@ -180,6 +180,36 @@ def main():
     err = float((y.float() - ref).abs().max() / ref.abs().max())
     expect(err < 2e-2, "bcast_gemm consumes the freshly broadcast weights (err {:.2e})".format(err))
 
+    # fault injection: a peer that never joins the collective must turn into an error status on the
+    # waiting ranks (bounded spin), not a hang -- and the session must be usable again afterwards
+    torch.manual_seed(0)
+    net = Net()
+    arena = ParamArena(net, dev)
+    sess = FedAvgSession(arena, n_ctas=8, timeout_log2=20)
+    timed_out = True
+    if rank != world - 1:                      # the last rank "dies": it skips this round
+        sess.aggregate(my_n=1.0)
+        torch.cuda.synchronize()
+        try:
+            sess.check()
+            timed_out = False
+        except RuntimeError:
+            timed_out = True
+    expect(timed_out, "dead peer -> timeout status instead of a hang")
+    ep = torch.tensor([sess.epoch], device=dev)
+    dist.all_reduce(ep, op=dist.ReduceOp.MAX)
+    sess.epoch = int(ep)
+    dist.broadcast(arena.theta, 0)
+    arena.commit_global()
+    torch.manual_seed(600 + rank)
+    arena.theta.add_(torch.randn_like(arena.theta) * 0.01)
+    thetas = gather_all(arena.theta.clone())
+    sess.aggregate(my_n=1.0)
+    torch.cuda.synchronize()
+    sess.check()
+    err = float((arena.theta - sum(thetas) / world).abs().max())
+    expect(err < 6e-4, "session recovers after the timeout (err {:.2e})".format(err))
+
     dist.barrier()
     if rank == 0:
         print("RESULT", "FAIL" if failures else "PASS", len(failures), flush=True)
