@@ -357,6 +357,152 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 
+// ---- persistent kernel: one CTA per SM walks the tile list; two TMEM accumulator stages let the
+// ---- epilogue of tile i overlap the main loop of tile i+1 (large problems: >= one wave of tiles) ----
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            const GemmParams p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator stage complete (MMA -> epilogue)
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator stage drained (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kt = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer: runs ahead across tile boundaries =====================
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // consecutive CTAs share the same N block (the B tile stays hot in L2) and walk M
+        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        for (int kt = 0; kt < num_kt; ++kt) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          const int k0 = kt * BK;
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[s], m0 + j * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    int s = 0;
+    uint32_t ph = 0;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int acc = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], aph ^ 1);   // the epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kt = 0; kt < num_kt; ++kt) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = p.a_mn ? umma_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                       : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = p.b_mn ? umma_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                       : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+            tc_mma_f16(d_tmem, ad, bd, idesc, (kt | k) != 0);
+          }
+          tc_commit(&empty_bar[s]);
+          if (kt == num_kt - 1) tc_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: drains stage `acc` while the MMA warp fills the other =====================
+    const int q = warp & 3;
+    const size_t elt = p.out_fp32 ? 4 : 2;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * elt) % 16 == 0);
+    int t = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+      const int acc = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      mbar_wait(&tfull_bar[acc], aph);
+      tc_fence_after();
+      const int row = m0 + q * 32 + static_cast<int>(lane_id());
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (row >= p.M || col0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        store_row_chunk<32>(p, row, col0, v, vec_ok);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+}
+
 // ---- runtime-depth pipeline + cluster split-K (DSMEM reduce) ----
 template <int BN, bool CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -622,6 +768,27 @@ static int launch_fixed(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
 }
 
 
+template <int BN, int STAGES>
+static int launch_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_tiles,
+                             cudaStream_t stream) {
+  constexpr int smem = STAGES * SmemLayout<BN>::STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static bool configured = false;
+  static int num_sms = 148;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_persistent_kernel<BN, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  cudaError_t le = launch_pdl(gemm_bf16_persistent_kernel<BN, STAGES>, dim3(grid), GEMM_THREADS, smem, stream, ta, tb, p);
+  if (le != cudaSuccess) return static_cast<int>(le);
+  return static_cast<int>(cudaGetLastError());
+}
+
 template <int BN>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
                       cudaStream_t stream) {
@@ -740,6 +907,17 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
     if (bn == 256) return launch_cfg<256>(ta, tb, p, grid, stream);
     if (bn == 128) return launch_cfg<128>(ta, tb, p, grid, stream);
     return launch_cfg<64>(ta, tb, p, grid, stream);
+  }
+  // large plain GEMMs (>= one wave of tiles, single K pass): persistent kernel with overlapped epilogue
+  static int persistent_on = -1;
+  if (persistent_on < 0) {
+    const char* e = std::getenv("BATON_GEMM_PERSISTENT");
+    persistent_on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const int num_tiles = static_cast<int>(grid.x * grid.y);
+  if (persistent_on && split_k == 1 && tile_flags == nullptr && num_tiles >= 148 && bn >= 128) {
+    if (bn == 256) return launch_persistent<256, 4>(ta, tb, p, num_tiles, stream);
+    return launch_persistent<128, 6>(ta, tb, p, num_tiles, stream);
   }
   if (bn == 256) return launch_fixed<256, 4>(ta, tb, p, grid, stream);
   if (bn == 128) return launch_fixed<128, 6>(ta, tb, p, grid, stream);

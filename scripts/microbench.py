@@ -44,7 +44,9 @@ print("torch add_ (native)   : {:6.2f} us/node".format(time_graph(lambda: t.add_
 shapes = [("stem  fwd", 32768, 64, 152, False, False), ("l1 fwd", 8192, 64, 576, False, False),
           ("l2 fwd", 2048, 128, 1152, False, False), ("l3 fwd", 512, 256, 2304, False, False),
           ("l4 fwd", 128, 512, 4608, False, False), ("l4 dgrad", 128, 4608, 512, False, True),
-          ("l1 dgrad", 8192, 576, 64, False, True), ("big", 8192, 8192, 8192, False, False)]
+          ("l1 dgrad", 8192, 576, 64, False, True), ("big", 8192, 8192, 8192, False, False),
+          ("bert qkv", 4096, 2304, 768, False, False), ("bert ffn1", 4096, 3072, 768, False, False),
+          ("bert ffn2", 4096, 768, 3072, False, False), ("bert dgrad", 4096, 768, 2304, False, True)]
 for name, M, N, K, amn, bmn in shapes:
     A = torch.randn(M, K, device=dev).to(BF16)
     B = (torch.randn(K, N, device=dev) if bmn else torch.randn(N, K, device=dev)).to(BF16)

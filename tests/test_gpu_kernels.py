@@ -109,6 +109,27 @@ def test_gemm_cluster_split_k_dsmem_reduce(F, S, M, N, K, bn):
         assert _rel(acc, A.float() @ B.float().t() + 1.0) < 2e-3
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(4096, 2304, 768), (4104, 2000, 520), (8192, 1024, 256)])
+def test_gemm_persistent_path(F, a_mn, b_mn, M, N, K):
+    """>= 148 output tiles: persistent CTAs, two TMEM accumulator stages (epilogue overlaps the next tile)."""
+    torch.manual_seed(M + N)
+    dev = _dev()
+    A = torch.randn(M, K, device=dev).to(BF16)
+    B = torch.randn(N, K, device=dev).to(BF16)
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    bias = torch.randn(N, device=dev)
+    ref = A.float() @ B.float().t()
+    out = F.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    assert _rel(out, ref) < 2e-3, _rel(out, ref)
+    out2 = F.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias, act=1)
+    assert _rel(out2, torch.relu(ref + bias)) < 1e-2
+    acc = torch.ones(M, N, device=dev)
+    F.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out=acc, accumulate=True, split_k=1)
+    assert _rel(acc, ref + 1.0) < 2e-3
+
+
 def test_gemm_simt_fallback_small_pitch(F):
     torch.manual_seed(2)
     dev = _dev()
