@@ -503,6 +503,196 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
 }
 
+// ---- 2-CTA persistent kernel: a CTA PAIR (cluster of 2, adjacent SMs) computes a 256 x BN tile with
+// ---- tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and only HALF of the B tile, the
+// ---- tensor cores of both SMs read both halves, so L2 -> SMEM traffic per FLOP drops by a third.
+// ---- Leader CTA (cluster rank 0) issues every MMA; both CTAs run TMA producers and epilogues.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// arrive on the barrier at the same smem offset in BOTH CTAs of the pair once the MMAs retire
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 0x3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const GemmParams p) {
+  constexpr int A_BYTES = BM * BK * 2;            // this CTA's 128 rows of A
+  constexpr int BH_BYTES = (BN / 2) * BK * 2;     // this CTA's half of the B tile
+  constexpr int STAGE = A_BYTES + BH_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);   // used in the leader only
+  uint64_t* empty_bar = full_bar + STAGES;                                   // both CTAs (multicast commit)
+  uint64_t* tfull_bar = empty_bar + STAGES;                                  // [2] both CTAs (multicast commit)
+  uint64_t* tempty_bar = tfull_bar + 2;                                      // [2] leader only, 8 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  griddep_launch_dependents();
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kt = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);   // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();      // barriers of both CTAs initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs): own A rows + own half of B =====================
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        const int m0 = (tile % tiles_m) * 2 * BM + static_cast<int>(rank) * BM;
+        const int n0 = (tile / tiles_m) * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kt = 0; kt < num_kt; ++kt) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE;
+          uint8_t* sb = sa + A_BYTES;
+          const int k0 = kt * BK;
+          const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);   // the LEADER's barrier collects both CTAs' bytes
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE);
+          if (!p.a_mn) {
+            tma_load_2d_2sm(sa, &tmA, lbar, k0, m0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &tmA, lbar, m0 + j * 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2sm(sb, &tmB, lbar, k0, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * 8192, &tmB, lbar, n0 + j * 64, k0);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader only): M = 256 across the pair =====================
+    const uint32_t idesc = umma_idesc_bf16(2 * BM, BN, p.a_mn, p.b_mn);
+    int s = 0;
+    uint32_t ph = 0;
+    int t = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs, ++t) {
+      const int acc = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kt = 0; kt < num_kt; ++kt) {
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + s * STAGE);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = p.a_mn ? umma_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                       : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = p.b_mn ? umma_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                       : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+            tc_mma_f16_2sm(d_tmem, ad, bd, idesc, (kt | k) != 0);
+          }
+          tc_commit_2sm(&empty_bar[s]);                       // frees the slot in BOTH CTAs
+          if (kt == num_kt - 1) tc_commit_2sm(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs): own 128 rows of the 256-row tile =====================
+    const int q = warp & 3;
+    const size_t elt = p.out_fp32 ? 4 : 2;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * elt) % 16 == 0);
+    int t = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs, ++t) {
+      const int acc = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      const int m0 = (tile % tiles_m) * 2 * BM + static_cast<int>(rank) * BM;
+      const int n0 = (tile / tiles_m) * BN;
+      mbar_wait(&tfull_bar[acc], aph);
+      tc_fence_after();
+      const int row = m0 + q * 32 + static_cast<int>(lane_id());
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (row >= p.M || col0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        store_row_chunk<32>(p, row, col0, v, vec_ok);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane_id() == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // tell the leader's MMA warp
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();      // the peer's smem / TMEM stay valid until the leader's last MMA has retired
+  if (warp == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+}
+
 // ---- runtime-depth pipeline + cluster split-K (DSMEM reduce) ----
 template <int BN, bool CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -769,6 +959,28 @@ static int launch_fixed(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
 
 
 template <int BN, int STAGES>
+static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_tiles,
+                       cudaStream_t stream) {
+  constexpr int stage = BM * BK * 2 + (BN / 2) * BK * 2;
+  constexpr int smem = STAGES * stage + (2 * STAGES + 4) * 8 + 16 + 1024;
+  static bool configured = false;
+  static int num_sms = 148;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_2cta_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  int pairs = num_sms / 2;
+  if (pairs > num_tiles) pairs = num_tiles;
+  cudaError_t le = launch_pdl(gemm_bf16_2cta_kernel<BN, STAGES>, dim3(2 * pairs), GEMM_THREADS, smem, stream, ta, tb, p);
+  if (le != cudaSuccess) return static_cast<int>(le);
+  return static_cast<int>(cudaGetLastError());
+}
+
+template <int BN, int STAGES>
 static int launch_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_tiles,
                              cudaStream_t stream) {
   constexpr int smem = STAGES * SmemLayout<BN>::STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
@@ -915,6 +1127,19 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
     persistent_on = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   const int num_tiles = static_cast<int>(grid.x * grid.y);
+  static int two_cta_on = -1;
+  if (two_cta_on < 0) {
+    const char* e = std::getenv("BATON_GEMM_2CTA");
+    two_cta_on = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  if (two_cta_on && split_k == 1 && tile_flags == nullptr && bn == 256 && num_tiles >= 148) {
+    // CTA pairs: 256 x 256 tiles, each CTA TMA-loads its 128 rows of A and its 128-row half of B
+    CUtensorMap tb2;
+    int rc2 = !b_mn ? make_map(&tb2, b, N, K, ldb, BK, 128) : make_map(&tb2, b, K, N, ldb, 64, BK);
+    if (rc2) return rc2;
+    const int tiles2 = ((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
+    return launch_2cta<256, 6>(ta, tb2, p, tiles2, stream);
+  }
   if (persistent_on && split_k == 1 && tile_flags == nullptr && num_tiles >= 148 && bn >= 128) {
     if (bn == 256) return launch_persistent<256, 4>(ta, tb, p, num_tiles, stream);
     return launch_persistent<128, 6>(ta, tb, p, num_tiles, stream);
