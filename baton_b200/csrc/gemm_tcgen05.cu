@@ -357,6 +357,82 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 
+// Epilogue of one 128 x BN accumulator stage for the persistent kernels.  TMEM rows land one per lane, so
+// direct stores would scatter 16 B pieces over 32 different output rows per instruction; instead each warp
+// stages 32 rows x 128 B in shared memory (pitch 144 B: conflict-free 16 B accesses) and writes them back
+// with lanes running along the row -- every store instruction covers four complete 128 B row segments.
+constexpr int EPI_PITCH = 144;
+constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH;
+
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int q, int m0, int n0,
+                                              uint8_t* stage, bool vec_ok) {
+  const int lane = static_cast<int>(lane_id());
+  const int row = m0 + q * 32 + lane;
+  const int elt = p.out_fp32 ? 4 : 2;
+  const bool fast = vec_ok && !p.atomic_out && (p.N % 8 == 0);
+  if (!fast) {
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c;
+      if (row >= p.M || col0 >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      store_row_chunk<32>(p, row, col0, v, vec_ok);
+    }
+    return;
+  }
+  const int W = 128 / elt;                          // output columns per 128-byte pass
+  uint8_t* srow = stage + lane * EPI_PITCH;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += W) {
+    if (n0 + c0 >= p.N) break;                      // warp-uniform
+    for (int cc = 0; cc < W; cc += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32b_x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c0 + cc, r);
+      tmem_ld_wait();
+      const int col0 = n0 + c0 + cc;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias != nullptr && (col0 + j) < p.N) x += p.bias[col0 + j];
+        v[j] = apply_act(x, p.act);
+      }
+      if (p.out_fp32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(srow + (cc + j) * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          *reinterpret_cast<uint4*>(srow + (cc + j) * 2) =
+              make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]), pack_bf16x2(v[j + 4], v[j + 5]),
+                         pack_bf16x2(v[j + 6], v[j + 7]));
+      }
+    }
+    __syncwarp();
+    const int per16 = 16 / elt;                     // columns per 16-byte chunk
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {                // 32 rows x 8 chunks = 256 chunks, 32 per instruction
+      const int idx = it * 32 + lane;
+      const int r = idx >> 3, ch = idx & 7;
+      const int grow = m0 + q * 32 + r;
+      const int col = n0 + c0 + ch * per16;
+      if (grow < p.M && col < p.N) {
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + r * EPI_PITCH + ch * 16);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.D) +
+                                  (static_cast<size_t>(grow) * p.ldd + col) * elt) = val;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ---- persistent kernel: one CTA per SM walks the tile list; two TMEM accumulator stages let the
 // ---- epilogue of tile i overlap the main loop of tile i+1 (large problems: >= one wave of tiles) ----
 template <int BN, int STAGES>
@@ -371,6 +447,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator stage complete (MMA -> epilogue)
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator stage drained (epilogue -> MMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(tmem_slot + 4);   // 4 warps x 32 rows x 144 B
 
   griddep_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -479,19 +556,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
-      const int row = m0 + q * 32 + static_cast<int>(lane_id());
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + c, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (row >= p.M || col0 >= p.N) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        store_row_chunk<32>(p, row, col0, v, vec_ok);
-      }
+      epilogue_tile<BN>(p, tmem_base + acc * BN, q, m0, n0, epi_stage + q * EPI_WARP_BYTES, vec_ok);
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
@@ -553,6 +618,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* tfull_bar = empty_bar + STAGES;                                  // [2] both CTAs (multicast commit)
   uint64_t* tempty_bar = tfull_bar + 2;                                      // [2] leader only, 8 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* epi_stage = reinterpret_cast<uint8_t*>(tmem_slot + 4);            // 4 warps x 32 rows x 144 B
 
   griddep_launch_dependents();
   const int warp = threadIdx.x >> 5;
@@ -668,19 +734,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int n0 = (tile / tiles_m) * BN;
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
-      const int row = m0 + q * 32 + static_cast<int>(lane_id());
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16) + c, r);
-        tmem_ld_wait();
-        const int col0 = n0 + c;
-        if (row >= p.M || col0 >= p.N) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        store_row_chunk<32>(p, row, col0, v, vec_ok);
-      }
+      epilogue_tile<BN>(p, tmem_base + acc * BN, q, m0, n0, epi_stage + q * EPI_WARP_BYTES, vec_ok);
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // tell the leader's MMA warp
@@ -962,7 +1016,7 @@ template <int BN, int STAGES>
 static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_tiles,
                        cudaStream_t stream) {
   constexpr int stage = BM * BK * 2 + (BN / 2) * BK * 2;
-  constexpr int smem = STAGES * stage + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * stage + (2 * STAGES + 4) * 8 + 16 + 4 * EPI_WARP_BYTES + 1024;
   static bool configured = false;
   static int num_sms = 148;
   if (!configured) {
@@ -983,7 +1037,7 @@ static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 template <int BN, int STAGES>
 static int launch_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int num_tiles,
                              cudaStream_t stream) {
-  constexpr int smem = STAGES * SmemLayout<BN>::STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * SmemLayout<BN>::STAGE_BYTES + (2 * STAGES + 4) * 8 + 16 + 4 * EPI_WARP_BYTES + 1024;
   static bool configured = false;
   static int num_sms = 148;
   if (!configured) {
