@@ -1184,9 +1184,13 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
   static int two_cta_on = -1;
   if (two_cta_on < 0) {
     const char* e = std::getenv("BATON_GEMM_2CTA");
-    two_cta_on = (e != nullptr && e[0] == '1') ? 1 : 0;
+    two_cta_on = (e == nullptr) ? 2 : (e[0] == '1' ? 1 : 0);   // unset: automatic, 1: whenever legal, 0: never
   }
-  if (two_cta_on && split_k == 1 && tile_flags == nullptr && bn == 256 && num_tiles >= 148) {
+  // measured (profiles/gemm_variants.md): pairs win once the K loop is long enough to amortise the
+  // cluster-scope handshakes (8192^3: 797 us vs 860 us) and lose on short-K BERT shapes (51 vs 31 us)
+  const int tiles_2cta = ((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
+  const bool two_cta_auto = two_cta_on == 2 && per >= 32 && tiles_2cta >= 2 * 74;
+  if ((two_cta_on == 1 || two_cta_auto) && split_k == 1 && tile_flags == nullptr && bn == 256 && num_tiles >= 148) {
     // CTA pairs: 256 x 256 tiles, each CTA TMA-loads its 128 rows of A and its 128-row half of B
     CUtensorMap tb2;
     int rc2 = !b_mn ? make_map(&tb2, b, N, K, ldb, BK, 128) : make_map(&tb2, b, K, N, ldb, 64, BK);

@@ -130,6 +130,25 @@ def test_gemm_persistent_path(F, a_mn, b_mn, M, N, K):
     assert _rel(acc, ref + 1.0) < 2e-3
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, True)])
+def test_gemm_two_cta_pairs(F, a_mn, b_mn):
+    """Deep-K, multi-wave problem: dispatched to the cta_group::2 kernel (CTA pairs share 256 x 256 tiles,
+    each CTA loads half of B, one elected thread issues the MMAs for both SMs)."""
+    torch.manual_seed(5)
+    dev = _dev()
+    M, N, K = 4096, 2560 - 8, 2048 + 64          # ragged N tile, K not a multiple of the stage count
+    A = torch.randn(M, K, device=dev).to(BF16)
+    B = torch.randn(N, K, device=dev).to(BF16)
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    bias = torch.randn(N, device=dev)
+    ref = A.float() @ B.float().t()
+    out = F.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32)
+    assert _rel(out, ref) < 2e-3, _rel(out, ref)
+    out2 = F.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias, act=1)
+    assert _rel(out2, torch.relu(ref + bias)) < 1e-2
+
+
 def test_gemm_simt_fallback_small_pitch(F):
     torch.manual_seed(2)
     dev = _dev()
