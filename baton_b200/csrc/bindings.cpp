@@ -194,7 +194,7 @@ void fedavg_allreduce(const std::vector<int64_t>& wire_ptrs, const std::vector<i
                       const std::optional<at::Tensor>& int_local, const std::vector<int64_t>& int_wire_ptrs,
                       const std::optional<at::Tensor>& loss_local, const std::vector<int64_t>& loss_wire_ptrs,
                       const std::optional<at::Tensor>& loss_out, const std::vector<double>& n_samples,
-                      bool counts_from_flags, int64_t alive_mask, int64_t rank, int64_t world, bool wire_bf16,
+                      bool counts_from_flags, int64_t alive_mask, int64_t rank, int64_t world, int64_t wire_kind,
                       bool delta, bool use_nvls, int64_t epoch, const std::optional<at::Tensor>& tile_flags,
                       int64_t flag_value, int64_t tile_elems, int64_t n_ctas, int64_t timeout_log2,
                       const std::optional<at::Tensor>& status) {
@@ -228,7 +228,7 @@ void fedavg_allreduce(const std::vector<int64_t>& wire_ptrs, const std::vector<i
   a.rank = static_cast<int>(rank);
   a.world = static_cast<int>(world);
   a.n = theta.numel();
-  a.wire_bf16 = wire_bf16;
+  a.wire_kind = static_cast<int>(wire_kind);
   a.delta = delta;
   a.use_nvls = use_nvls;
   a.epoch = static_cast<uint32_t>(epoch);

@@ -1,5 +1,6 @@
 // Fused FedAvg collective over NVLink 5 / NVSwitch -- ONE persistent kernel per round that does
 //
+//   (wire formats: fp32, bf16, or block-scaled fp8 = e4m3 + one UE8M0 scale per 32 elements)
 //   phase 0  pack      wire_r[t]  = cast( s_r * (theta_r[t] - global[t]) )   (delta mode)
 //                                   cast( s_r * theta_r[t] )                 (weights mode)
 //   barrier  per-CTA 64-bit flags in peer-mapped pads, st.release.sys / ld.acquire.sys; the flag
@@ -32,6 +33,7 @@
 // peer that dies mid-collective into an error status instead of a hang.
 #include "ptx.cuh"
 #include "launch.h"
+#include "mx.cuh"
 
 namespace b200 {
 
@@ -74,43 +76,105 @@ __device__ __forceinline__ bool cta_barrier_all_ranks(const FedAvgArgs& a, uint3
   return all_ok != 0;
 }
 
-template <bool WIRE_BF16>
+__device__ __forceinline__ uint2 ld_volatile_v2(const void* p) {
+  uint2 r;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_na_v2(void* p, const uint2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_volatile_u8(const void* p) {
+  uint32_t r;
+  asm volatile("ld.volatile.global.u8 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_volatile_u8(void* p, uint32_t v) {
+  asm volatile("st.volatile.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Wire formats.  WIRE 0: fp32 (4 per 16 B), 1: bf16 (8 per 16 B), 2: MXFP8 -- e4m3 payload (8 per 8 B
+// thread vector) plus one UE8M0 scale byte per 32 consecutive elements, stored behind the payload.
+template <int WIRE>
 struct Wire;
 template <>
-struct Wire<true> {  // 8 bf16 per 16 B
-  static constexpr int VEC = 8;
-  __device__ static void unpack(const uint4& u, float (&f)[8]) {
+struct Wire<1> {
+  static constexpr int VEC = 8, VBYTES = 16;
+  static constexpr bool SCALED = false;
+  __device__ static void unpack(const uint4& u, float (&f)[8], float) {
     float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
   }
-  __device__ static uint4 pack(const float (&f)[8]) {
+  __device__ static uint4 pack(const float (&f)[8], float) {
     uint4 u;
     u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
     u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
     return u;
   }
+  __device__ static uint4 ld(const void* p) { return ld_volatile_v4(p); }
+  __device__ static void st(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+  __device__ static void st_na(void* p, const uint4& v) { st_na_v4(p, v); }
   __device__ static uint4 mc_reduce(const void* p) { return multimem_ld_reduce_bf16x8(p); }
 };
 template <>
-struct Wire<false> {  // 4 fp32 per 16 B
-  static constexpr int VEC = 4;
-  __device__ static void unpack(const uint4& u, float (&f)[4]) {
+struct Wire<0> {
+  static constexpr int VEC = 4, VBYTES = 16;
+  static constexpr bool SCALED = false;
+  __device__ static void unpack(const uint4& u, float (&f)[4], float) {
     f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y);
     f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
   }
-  __device__ static uint4 pack(const float (&f)[4]) {
+  __device__ static uint4 pack(const float (&f)[4], float) {
     return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
   }
+  __device__ static uint4 ld(const void* p) { return ld_volatile_v4(p); }
+  __device__ static void st(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+  __device__ static void st_na(void* p, const uint4& v) { st_na_v4(p, v); }
   __device__ static uint4 mc_reduce(const void* p) {
     float4 r = multimem_ld_reduce_f32x4(p);
     return make_uint4(__float_as_uint(r.x), __float_as_uint(r.y), __float_as_uint(r.z), __float_as_uint(r.w));
   }
 };
+template <>
+struct Wire<2> {
+  static constexpr int VEC = 8, VBYTES = 8;
+  static constexpr bool SCALED = true;
+  __device__ static void unpack(const uint4& u, float (&f)[8], float scale) {
+    const float2 a = from_e4m3x2(static_cast<uint16_t>(u.x & 0xFFFFu)), b = from_e4m3x2(static_cast<uint16_t>(u.x >> 16));
+    const float2 c = from_e4m3x2(static_cast<uint16_t>(u.y & 0xFFFFu)), d = from_e4m3x2(static_cast<uint16_t>(u.y >> 16));
+    f[0] = a.x * scale; f[1] = a.y * scale; f[2] = b.x * scale; f[3] = b.y * scale;
+    f[4] = c.x * scale; f[5] = c.y * scale; f[6] = d.x * scale; f[7] = d.y * scale;
+  }
+  __device__ static uint4 pack(const float (&f)[8], float inv) {
+    uint4 u;
+    u.x = to_e4m3x2(f[0] * inv, f[1] * inv) | (static_cast<uint32_t>(to_e4m3x2(f[2] * inv, f[3] * inv)) << 16);
+    u.y = to_e4m3x2(f[4] * inv, f[5] * inv) | (static_cast<uint32_t>(to_e4m3x2(f[6] * inv, f[7] * inv)) << 16);
+    u.z = 0; u.w = 0;
+    return u;
+  }
+  __device__ static uint4 ld(const void* p) { const uint2 v = ld_volatile_v2(p); return make_uint4(v.x, v.y, 0, 0); }
+  __device__ static void st(void* p, const uint4& v) { *reinterpret_cast<uint2*>(p) = make_uint2(v.x, v.y); }
+  __device__ static void st_na(void* p, const uint4& v) { st_na_v2(p, make_uint2(v.x, v.y)); }
+  __device__ static uint4 mc_reduce(const void*) { return make_uint4(0, 0, 0, 0); }   // the switch cannot apply block scales
+};
 
-template <bool WIRE_BF16>
+// shared exponent of the 32-element block owned by a quad of adjacent lanes (8 elements each);
+// every lane of the warp must call this
+template <int VEC>
+__device__ __forceinline__ int quad_block_exponent(const float (&f)[VEC]) {
+  float amax = 0.f;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) amax = fmaxf(amax, fabsf(f[j]));
+  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+  return mx_exponent(amax);
+}
+
+template <int WIRE>
 __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(const __grid_constant__ FedAvgArgs a) {
-  using W = Wire<WIRE_BF16>;
+  using W = Wire<WIRE>;
   constexpr int VEC = W::VEC;
+  constexpr bool SCALED = W::SCALED;
   const int G = gridDim.x;
   __shared__ uint8_t* s_wire[B200_MAX_RANKS];   // indexed by position among the live ranks
   __shared__ long long* s_int[B200_MAX_RANKS];
@@ -136,7 +200,9 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
   const int T = a.tile_elems;
   const long long n_tiles = (n + T - 1) / T;
   const float my_n = a.n_samples[a.rank];
-  const size_t esz = WIRE_BF16 ? 2 : 4;
+  constexpr size_t esz = W::VBYTES / VEC;         // payload bytes per element
+  const size_t sc_off = static_cast<size_t>(n);   // SCALED: scale bytes live behind the n payload bytes
+  const int lane_elems = static_cast<int>(threadIdx.x & 31) * VEC;
   uint8_t* my_wire = reinterpret_cast<uint8_t*>(a.wire[a.rank]);
   const float* __restrict__ theta_r = a.theta;
   const float* __restrict__ global_r = a.global_w;
@@ -144,6 +210,7 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
   // ---------------------------------------------------------------- phase 0: pack (+ prescale) + cast
   // P2P mode applies w_k on the reader side (the upload keeps full wire precision); NVLS mode needs
   // the scaled value on the wire because the switch can only add: scale by n_k now, by 1/N in phase 2.
+  // Loop bounds are warp-uniform (first lane's element) so the block-scale shuffles are legal.
   const float pack_scale = a.use_nvls ? my_n * a.nvls_prescale : 1.0f;
   if (my_n != 0.f || a.use_nvls) {
     for (long long q = blockIdx.x; q * A < n_tiles; q += G) {
@@ -153,8 +220,8 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
         const long long base = t * T;
         const int len = static_cast<int>((n - base) < T ? (n - base) : T);
         constexpr int STEP = FEDAVG_THREADS * VEC;
-        for (int i0 = threadIdx.x * VEC; i0 < len; i0 += 2 * STEP) {
-          // two independent 16 B wire vectors per trip, every load issued before the first store
+        for (int i0 = threadIdx.x * VEC; i0 - lane_elems < len; i0 += 2 * STEP) {
+          // two independent wire vectors per trip, every load issued before the first store
           float4 th[2][VEC / 4], gg[2][VEC / 4];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -170,8 +237,11 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int i = i0 + u * STEP;
-            if (i < len) {
-              float f[VEC];
+            const bool valid = i < len;
+            float f[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) f[j] = 0.f;
+            if (valid) {
 #pragma unroll
               for (int j = 0; j < VEC; j += 4) {
                 float4 t4 = th[u][j >> 2];
@@ -182,8 +252,16 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
                 f[j] = t4.x * pack_scale; f[j + 1] = t4.y * pack_scale;
                 f[j + 2] = t4.z * pack_scale; f[j + 3] = t4.w * pack_scale;
               }
-              *reinterpret_cast<uint4*>(my_wire + (base + i) * esz) = W::pack(f);
             }
+            float inv = 1.f;
+            if constexpr (SCALED) {
+              if (i0 + u * STEP - lane_elems < len) {          // warp-uniform
+                const int e = quad_block_exponent<VEC>(f);
+                inv = exp2_int(-e);
+                if (valid && (threadIdx.x & 3) == 0) my_wire[sc_off + ((base + i) >> 5)] = static_cast<uint8_t>(e + 127);
+              }
+            }
+            if (valid) W::st(my_wire + (base + i) * esz, W::pack(f, inv));
           }
         }
       }
@@ -214,41 +292,65 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
   for (long long t = my_pos + static_cast<long long>(blockIdx.x) * A; t < n_tiles; t += static_cast<long long>(G) * A) {
     const long long base = t * T;
     const int len = static_cast<int>((n - base) < T ? (n - base) : T);
-    for (int i = threadIdx.x * VEC; i < len; i += FEDAVG_THREADS * VEC) {
+    for (int i = threadIdx.x * VEC; i - lane_elems < len; i += FEDAVG_THREADS * VEC) {
+      const bool valid = i < len;
       const size_t off = (base + i) * esz;
+      const size_t sc_idx = sc_off + ((base + i) >> 5);
       uint4 out;
-      if (a.use_nvls) {
-        out = W::mc_reduce(reinterpret_cast<const uint8_t*>(a.wire_mc) + off);  // the switch adds the replicas
-        multimem_st_v4(reinterpret_cast<uint8_t*>(a.wire_mc) + off, out);       // the switch replicates the store
+      if (!SCALED && a.use_nvls) {
+        if (valid) {
+          out = W::mc_reduce(reinterpret_cast<const uint8_t*>(a.wire_mc) + off);  // the switch adds the replicas
+          multimem_st_v4(reinterpret_cast<uint8_t*>(a.wire_mc) + off, out);       // the switch replicates the store
+        }
       } else {
         // peers in groups of 8 (one NVSwitch box): issue the group's loads first (memory-level
         // parallelism), then accumulate in fixed rank order so the result is bitwise reproducible
         float acc[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        if (valid) {
 #pragma unroll 1
-        for (int k0 = 0; k0 < A; k0 += 8) {
-          uint4 v[8];
+          for (int k0 = 0; k0 < A; k0 += 8) {
+            uint4 v[8];
+            uint32_t sc[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (k0 + k < A && s_w[k0 + k] != 0.f) v[k] = ld_volatile_v4(s_wire[k0 + k] + off);
+            for (int k = 0; k < 8; ++k)
+              if (k0 + k < A && s_w[k0 + k] != 0.f) {
+                v[k] = W::ld(s_wire[k0 + k] + off);
+                if constexpr (SCALED) sc[k] = ld_volatile_u8(s_wire[k0 + k] + sc_idx);
+              }
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (k0 + k < A) {
-              const float w = s_w[k0 + k];
-              if (w != 0.f) {
-                float f[VEC];
-                W::unpack(v[k], f);
+            for (int k = 0; k < 8; ++k) {
+              if (k0 + k < A) {
+                const float w = s_w[k0 + k];
+                if (w != 0.f) {
+                  float f[VEC];
+                  float scale = 1.f;
+                  if constexpr (SCALED) scale = exp2_int(static_cast<int>(sc[k]) - 127);
+                  W::unpack(v[k], f, scale);
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, f[j], acc[j]);
+                  for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, f[j], acc[j]);
+                }
               }
             }
           }
         }
-        out = W::pack(acc);
+        float inv = 1.f;
+        int e = 0;
+        if constexpr (SCALED) {
+          e = quad_block_exponent<VEC>(acc);     // every lane of the warp arrives here
+          inv = exp2_int(-e);
+        }
+        if (valid) {
+          out = W::pack(acc, inv);
 #pragma unroll
-        for (int k = 0; k < B200_MAX_RANKS; ++k)
-          if (k < A) st_na_v4(s_wire[k] + off, out);
+          for (int k = 0; k < B200_MAX_RANKS; ++k)
+            if (k < A) {
+              W::st_na(s_wire[k] + off, out);
+              if constexpr (SCALED)
+                if ((threadIdx.x & 3) == 0) st_volatile_u8(s_wire[k] + sc_idx, static_cast<uint32_t>(e + 127));
+            }
+        }
       }
     }
   }
@@ -275,12 +377,14 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
       constexpr int STEP = FEDAVG_THREADS * VEC;
       for (int i0 = threadIdx.x * VEC; i0 < len; i0 += 2 * STEP) {
         uint4 wv[2];
+        uint32_t sc[2];
         float4 gg[2][VEC / 4];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int i = i0 + u * STEP;
           if (i < len) {
-            wv[u] = ld_volatile_v4(my_wire + (base + i) * esz);
+            wv[u] = W::ld(my_wire + (base + i) * esz);
+            if constexpr (SCALED) sc[u] = ld_volatile_u8(my_wire + sc_off + ((base + i) >> 5));
             if (a.delta) {
 #pragma unroll
               for (int j = 0; j < VEC; j += 4) gg[u][j >> 2] = *reinterpret_cast<const float4*>(a.global_w + base + i + j);
@@ -292,7 +396,9 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
           const int i = i0 + u * STEP;
           if (i < len) {
             float f[VEC];
-            W::unpack(wv[u], f);
+            float scale = 1.f;
+            if constexpr (SCALED) scale = exp2_int(static_cast<int>(sc[u]) - 127);
+            W::unpack(wv[u], f, scale);
 #pragma unroll
             for (int j = 0; j < VEC; j += 4) {
               float4 nw = make_float4(f[j] * apply_scale, f[j + 1] * apply_scale, f[j + 2] * apply_scale,
@@ -358,10 +464,15 @@ extern "C" int b200_fedavg_allreduce(const FedAvgArgs* args, int n_ctas, cudaStr
   using namespace b200;
   if (args->world > B200_MAX_RANKS || args->n % 8 != 0 || args->tile_elems % 8 != 0) return -2;
   if (n_ctas < 1) n_ctas = 1;
-  if (args->wire_bf16)
-    fedavg_allreduce_kernel<true><<<n_ctas, FEDAVG_THREADS, 0, stream>>>(*args);
-  else
-    fedavg_allreduce_kernel<false><<<n_ctas, FEDAVG_THREADS, 0, stream>>>(*args);
+  if (args->wire_kind == 2) {
+    // block-scaled fp8 wire: 32-element blocks must not straddle tiles, and the switch cannot rescale
+    if (args->tile_elems % 32 != 0 || args->use_nvls) return -2;
+    fedavg_allreduce_kernel<2><<<n_ctas, FEDAVG_THREADS, 0, stream>>>(*args);
+  } else if (args->wire_kind == 1) {
+    fedavg_allreduce_kernel<1><<<n_ctas, FEDAVG_THREADS, 0, stream>>>(*args);
+  } else {
+    fedavg_allreduce_kernel<0><<<n_ctas, FEDAVG_THREADS, 0, stream>>>(*args);
+  }
   return static_cast<int>(cudaGetLastError());
 }
 

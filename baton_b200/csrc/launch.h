@@ -74,7 +74,7 @@ struct FedAvgArgs {
   int rank, world;
   long long n;                      // float elements in the arena
   int n_int;
-  int wire_bf16;                    // 1: wire dtype bf16, 0: fp32
+  int wire_kind;                    // 0: fp32 wire, 1: bf16, 2: block-scaled fp8 (e4m3 + UE8M0 / 32)
   int delta;                        // 1: upload theta - global, result applied as global += sum
   int use_nvls;                     // 1: multimem.ld_reduce / multimem.st on wire_mc
   uint32_t epoch;                   // barrier epoch base (this launch uses epoch+1 .. epoch+3)

@@ -69,6 +69,7 @@ class _WgradOverlap:
     def __init__(self):
         import os
         self.enabled = os.environ.get("BATON_WGRAD_OVERLAP", "1") != "0"
+        self.max_flops = float(os.environ.get("BATON_WGRAD_OVERLAP_MAX_GFLOP", "4")) * 1e9
         self.streams = {}
         self.keep = []
         self.pending = False
@@ -76,6 +77,10 @@ class _WgradOverlap:
 
     def run(self, fn, *keep):
         if not self.enabled or not keep[0].is_cuda:
+            return fn()
+        # dY[M, N] x X[M, K]: a GEMM that fills the machine on its own gains nothing from a parallel branch and
+        # would only fight the persistent (one CTA per SM) dgrad kernels for SMs
+        if 2.0 * keep[0].shape[0] * keep[0].shape[-1] * keep[1].shape[-1] > self.max_flops:
             return fn()
         dev = keep[0].device
         side = self.streams.get(dev)

@@ -36,19 +36,20 @@ class FedAvgSession:
                  reset_momentum: bool = True, tile_flags: bool = False):
         from ..ops._ext import load
         self._C = load()
-        assert wire_dtype in ("bf16", "fp32") and mode in ("delta", "weights")
+        assert wire_dtype in ("bf16", "fp32", "fp8") and mode in ("delta", "weights")
         self.arena = arena
         self.device = arena.device
         self.group = group
+        self.wire_dtype = wire_dtype
         self.wire_bf16 = wire_dtype == "bf16"
+        self.wire_kind = {"fp32": 0, "bf16": 1, "fp8": 2}[wire_dtype]
         self.delta = mode == "delta"
         self.n_ctas = max(1, min(int(n_ctas), MAX_CTAS))
         self.tile_elems = int(tile_elems)
         self.timeout_log2 = int(timeout_log2)
         self.reset_momentum = reset_momentum
-        esz = 2 if self.wire_bf16 else 4
         self.off_wire = 0
-        self.off_int = _align(arena.n * esz, 256)
+        self.off_int = _align(self.wire_bytes(), 256)
         self.off_loss = _align(self.off_int + max(arena.n_int, 1) * 8, 256)
         self.off_pads = _align(self.off_loss + MAX_LOSS * 4, 256)
         total = _align(self.off_pads + (MAX_CTAS + 8) * self._C.MAX_RANKS * 8, 2 << 20)
@@ -56,6 +57,8 @@ class FedAvgSession:
         self.rank, self.world = self.symm.rank, self.symm.world
         assert self.world <= self._C.MAX_RANKS
         self.use_nvls = self.symm.has_multicast if nvls == "auto" else (bool(nvls) and self.symm.has_multicast)
+        if self.wire_kind == 2:
+            self.use_nvls = False      # the switch adds raw elements; block scales need the P2P path
         self.epoch = 0
         self.rounds = 0
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -103,7 +106,7 @@ class FedAvgSession:
             tile = self.tile_elems
         else:   # one tile per (live rank, CTA): n / (A * G), rounded up to a multiple of 8 elements
             per = -(-a.n // (len(alive) * self.n_ctas))
-            tile = max(self.min_tile, (per + 7) // 8 * 8)
+            tile = max(self.min_tile, (per + 31) // 32 * 32)
         self.last_tile_elems = tile
         flag_value = self.rounds + 1
         cur = torch.cuda.current_stream(self.device)
@@ -119,7 +122,7 @@ class FedAvgSession:
                 a.int_arena if a.n_int > 0 else None,
                 self.symm.peer_ptrs(self.off_int) if a.n_int > 0 else [],
                 self.loss_local, self.symm.peer_ptrs(self.off_loss), self.loss_out,
-                counts, from_flags, mask, self.rank, world, self.wire_bf16, self.delta,
+                counts, from_flags, mask, self.rank, world, self.wire_kind, self.delta,
                 bool(self.use_nvls and len(alive) == world), self.epoch,
                 self.tile_flags, flag_value, tile, self.n_ctas, self.timeout_log2, self.status)
         self.epoch = (self.epoch + 3) & 0xFFFFFFFF     # uint32 wrap: the kernel compares signed differences
@@ -168,7 +171,11 @@ class FedAvgSession:
             raise RuntimeError("FedAvg collective timed out waiting for rank {}".format(code - 1))
 
     def wire_bytes(self) -> int:
-        return self.arena.n * (2 if self.wire_bf16 else 4)
+        """Bytes one client uploads per round (fp8: e4m3 payload + one UE8M0 scale byte per 32 elements)."""
+        n = self.arena.n
+        if self.wire_kind == 2:
+            return n + (n + 31) // 32
+        return n * (2 if self.wire_kind == 1 else 4)
 
 
 class NcclSession:

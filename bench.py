@@ -42,7 +42,8 @@ def parse_args(argv=None):
     ap.add_argument("--lr", type=float, default=0.05)
     ap.add_argument("--momentum", type=float, default=0.0)
     ap.add_argument("--alpha", type=float, default=0.5, help="Dirichlet label skew of the shards")
-    ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--wire", default="bf16", choices=["bf16", "fp32", "fp8"],
+                    help="wire format of the fused FedAvg collective (fp8 = e4m3 + UE8M0 scale per 32 elements)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8"],
                     help="fp8 = block-scaled MXFP8 convolutions (fwd/dgrad/wgrad), everything else bf16/fp32")
     ap.add_argument("--backend", default="fused", choices=["fused", "nccl"])

@@ -32,10 +32,10 @@ def main():
     rows = []
     ctas_list = [int(x) for x in os.environ.get("AGG_CTAS", "148").split(",")]
     for name, n in SIZES.items():
-        for wire in ("bf16", "fp32"):
-            variants = [("nccl", None, 0)]
+        for wire in ("bf16", "fp32", "fp8"):
+            variants = [("nccl", None, 0)] if wire != "fp8" else []      # NCCL has no block-scaled wire
             for c in ctas_list:
-                variants += [("fused-p2p", False, c), ("fused-nvls", True, c)]
+                variants += [("fused-p2p", False, c)] + ([("fused-nvls", True, c)] if wire != "fp8" else [])
             for label, nvls, ctas in variants:
                 arena = ParamArena(Blob(n), dev)
                 arena.theta.normal_()
@@ -62,7 +62,7 @@ def main():
                 t = torch.tensor([min(times), sum(times) / len(times)], device=dev, dtype=torch.float64)
                 if world > 1:
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                wire_bytes = arena.n * (2 if wire == "bf16" else 4)
+                wire_bytes = arena.n * (2 if wire == "bf16" else 4) if wire != "fp8" else arena.n + arena.n // 32
                 if world > 1:
                     floor = (world - 1) / world * wire_bytes / 770e9 * 1e6
                     bound = "nvlink770"
