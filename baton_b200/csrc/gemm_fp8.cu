@@ -219,22 +219,32 @@ gemm_fp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int col0 = n0 + c;
       if (!row_ok || col0 >= p.N) continue;
       float v[32];
+      // (bias, activation) resolved once per chunk by warp-uniform branches, then straight-line code
+      if (p.bias != nullptr) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias != nullptr && (col0 + j) < p.N) x += p.bias[col0 + j];
-        v[j] = f8_act(x, p.act);
+        for (int j = 0; j < 32; ++j)
+          v[j] = fmaf(__uint_as_float(r[j]), p.alpha, (col0 + j) < p.N ? __ldg(p.bias + col0 + j) : 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.act != 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = f8_act(v[j], p.act);
       }
       const bool full = (col0 + 32 <= p.N);
       if (p.out_fp32) {
         float* d = reinterpret_cast<float*>(drow) + col0;
         if (p.atomic_out) {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) atomicAdd(d + j, v[j]);
+          _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) atomicAdd(d + j, v[j]);
         } else if (full && vec_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) d[j] = v[j];
+          _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) d[j] = v[j];
         }
       } else {
         __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(drow) + col0;
@@ -244,7 +254,7 @@ gemm_fp8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             *reinterpret_cast<uint4*>(d + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
                                                           pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
         } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) d[j] = __float2bfloat16_rn(v[j]);
+          _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) d[j] = __float2bfloat16_rn(v[j]);
         }
       }
     }

@@ -45,6 +45,7 @@ struct GemmParams {
   const float* bias;      // [N] or nullptr
   int out_fp32;           // 1: D is fp32, 0: D is bf16
   int act;                // 0 none, 1 relu, 2 gelu(tanh)
+  int epi_staged;         // persistent kernels: 1 = smem-staged row-coalesced stores, 0 = direct per-lane stores
   int a_mn, b_mn;         // operand majors
   int k_tiles_per_split;  // split-K: k tiles handled by one z-slice
   int atomic_out;         // 1: red.add fp32 into D
@@ -103,14 +104,53 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t
 }
 
 // bias + activation + cast + store of `NV` consecutive output columns of one row
-template <int NV>
-__device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, int col0, float (&v)[NV], bool vec_ok) {
+// alpha / bias / activation of one row chunk.  The (activation, bias) combination is resolved ONCE per chunk
+// with warp-uniform branches into fully unrolled straight-line code; the per-element runtime switch this
+// replaces cost ~900 SASS instructions per 32-column chunk (ncu: profiles/r1_ncu_gemm_qkv_epilogue.txt).
+template <int NV, int ACT, bool BIAS>
+__device__ __forceinline__ void transform_chunk_t(const GemmParams& p, int col0, float (&v)[NV]) {
+  float b[NV];
+  if (BIAS) {
+    if (col0 + NV <= p.N && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 4) {      // every lane reads the same addresses: one broadcast request each
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) b[j] = (col0 + j) < p.N ? __ldg(p.bias + col0 + j) : 0.f;
+    }
+  }
+  const float alpha = p.alpha;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    float x = v[j] * p.alpha;
-    if (p.bias != nullptr && (col0 + j) < p.N) x += p.bias[col0 + j];
-    v[j] = apply_act(x, p.act);
+    float x = v[j] * alpha;
+    if (BIAS) x += b[j];
+    if (ACT == 1) x = fmaxf(x, 0.f);
+    if (ACT == 2) {
+      const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+      x = 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
+    }
+    v[j] = x;
   }
+}
+template <int NV>
+__device__ __forceinline__ void transform_chunk(const GemmParams& p, int col0, float (&v)[NV]) {
+  if (p.bias == nullptr) {
+    if (p.act == 0) transform_chunk_t<NV, 0, false>(p, col0, v);
+    else if (p.act == 1) transform_chunk_t<NV, 1, false>(p, col0, v);
+    else transform_chunk_t<NV, 2, false>(p, col0, v);
+  } else {
+    if (p.act == 0) transform_chunk_t<NV, 0, true>(p, col0, v);
+    else if (p.act == 1) transform_chunk_t<NV, 1, true>(p, col0, v);
+    else transform_chunk_t<NV, 2, true>(p, col0, v);
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, int col0, float (&v)[NV], bool vec_ok) {
+  transform_chunk<NV>(p, col0, v);
   const bool full = (col0 + NV <= p.N);
   if (p.out_fp32) {
     float* d = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
@@ -122,13 +162,13 @@ __device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, in
                        "f"(v[j + 2]), "f"(v[j + 3])
                        : "memory");
       } else {
-        for (int j = 0; j < NV && col0 + j < p.N; ++j) atomicAdd(d + j, v[j]);
+        _Pragma("unroll") for (int j = 0; j < NV; ++j) if (col0 + j < p.N) atomicAdd(d + j, v[j]);
       }
     } else if (full && vec_ok) {
 #pragma unroll
       for (int j = 0; j < NV; j += 4) *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     } else {
-      for (int j = 0; j < NV && col0 + j < p.N; ++j) d[j] = v[j];
+      _Pragma("unroll") for (int j = 0; j < NV; ++j) if (col0 + j < p.N) d[j] = v[j];
     }
   } else {
     __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
@@ -143,7 +183,7 @@ __device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, in
         *reinterpret_cast<uint4*>(d + j) = o;
       }
     } else {
-      for (int j = 0; j < NV && col0 + j < p.N; ++j) d[j] = __float2bfloat16_rn(v[j]);
+      _Pragma("unroll") for (int j = 0; j < NV; ++j) if (col0 + j < p.N) d[j] = __float2bfloat16_rn(v[j]);
     }
   }
 }
@@ -306,11 +346,8 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (!row_ok || col0 >= p.N) continue;
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias != nullptr && (col0 + j) < p.N) x += p.bias[col0 + j];
-        v[j] = apply_act(x, p.act);
-      }
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      transform_chunk<32>(p, col0, v);
       const bool full = (col0 + 32 <= p.N);
       if (p.atomic_out) {
         float* d = reinterpret_cast<float*>(drow) + col0;
@@ -321,7 +358,7 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                          "f"(v[j + 2]), "f"(v[j + 3])
                          : "memory");
         } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) atomicAdd(d + j, v[j]);
+          _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) atomicAdd(d + j, v[j]);
         }
       } else if (p.out_fp32) {
         float* d = reinterpret_cast<float*>(drow) + col0;
@@ -330,7 +367,7 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(d + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) d[j] = v[j];
+          _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) d[j] = v[j];
         }
       } else {
         __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(drow) + col0;
@@ -345,7 +382,7 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             *reinterpret_cast<uint4*>(d + j) = o;
           }
         } else {
-          for (int j = 0; j < 32 && col0 + j < p.N; ++j) d[j] = __float2bfloat16_rn(v[j]);
+          _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) d[j] = __float2bfloat16_rn(v[j]);
         }
       }
     }
@@ -370,7 +407,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   const int lane = static_cast<int>(lane_id());
   const int row = m0 + q * 32 + lane;
   const int elt = p.out_fp32 ? 4 : 2;
-  const bool fast = vec_ok && !p.atomic_out && (p.N % 8 == 0);
+  const bool fast = p.epi_staged && vec_ok && !p.atomic_out && (p.N % 8 == 0);
   if (!fast) {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
@@ -398,11 +435,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       const int col0 = n0 + c0 + cc;
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias != nullptr && (col0 + j) < p.N) x += p.bias[col0 + j];
-        v[j] = apply_act(x, p.act);
-      }
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      transform_chunk<32>(p, col0, v);
       if (p.out_fp32) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -1161,6 +1195,12 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
   p.a_mn = a_mn; p.b_mn = b_mn; p.k_tiles_per_split = per;
   p.cluster_k = cluster_k;
   p.atomic_out = (accumulate || (split_k > 1 && cluster_k == 1)) ? 1 : 0;
+  static int epi_staged = -1;
+  if (epi_staged < 0) {
+    const char* e = std::getenv("BATON_GEMM_EPI_STAGED");
+    epi_staged = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  p.epi_staged = epi_staged;
   p.tile_flags = tile_flags; p.flag_epoch = flag_epoch; p.alpha = alpha;
   p.flag_elem_off = flag_elem_off; p.flag_tile_elems = flag_tile_elems; p.ldb = ldb;
   p.flag_bias_off = (tile_flags != nullptr && bias != nullptr) ? flag_bias_off : -1;
@@ -1239,6 +1279,7 @@ extern "C" int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int
   p.M = M; p.N = N; p.K = K; p.D = d; p.ldd = ldd; p.bias = nullptr; p.out_fp32 = out_fp32; p.act = act;
   p.a_mn = a_mn; p.b_mn = b_mn; p.k_tiles_per_split = (K + BK - 1) / BK; p.cluster_k = 1;
   p.atomic_out = accumulate ? 1 : 0;
+  p.epi_staged = 0;
   p.tile_flags = nullptr; p.flag_epoch = 0; p.alpha = alpha; p.flag_elem_off = 0; p.flag_tile_elems = 0;
   p.ldb = ldb; p.flag_bias_off = -1; p.stages = 4;
   p.batched = 1; p.batch_inner = n_inner; p.d_outer = d_outer; p.d_inner = d_inner;

@@ -8,8 +8,8 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from baton_b200.data import ShardSpec, image_shard  # noqa: E402
-from baton_b200.models import resnet18, resnet50  # noqa: E402
+from baton_b200.data import ShardSpec, image_shard, token_shard  # noqa: E402
+from baton_b200.models import bert_base, resnet18, resnet50  # noqa: E402
 from baton_b200.parallel.arena import ParamArena  # noqa: E402
 from baton_b200.parallel.fedavg import FedAvgSession  # noqa: E402
 from baton_b200.train import GraphedLocalSGD  # noqa: E402
@@ -22,11 +22,16 @@ ap.add_argument("--agg", type=int, default=2)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-m = resnet18(10) if args.model == "resnet18" else resnet50(10)
+is_bert = args.model == "bert_base"
+m = bert_base(2) if is_bert else (resnet18(10) if args.model == "resnet18" else resnet50(10))
 arena = ParamArena(m, dev)
-m.build_workspace(dev)
+if not is_bert:
+    m.build_workspace(dev)
 tr = GraphedLocalSGD(m, arena, loss="ce", use_graph=False)
-X, y = image_shard(ShardSpec(0, torch.full((10,), 0.1), args.batch_size * args.steps), dtype=torch.bfloat16)
+if is_bert:
+    X, y = token_shard(ShardSpec(0, torch.full((2,), 0.5), args.batch_size * args.steps), seq_len=128)
+else:
+    X, y = image_shard(ShardSpec(0, torch.full((10,), 0.1), args.batch_size * args.steps), dtype=torch.bfloat16)
 X, y = X.to(dev), y.to(dev)
 tr.run(X, y, n_epoch=1, lr=0.05, batch_size=args.batch_size)
 sess = FedAvgSession(arena)

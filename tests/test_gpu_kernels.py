@@ -331,6 +331,38 @@ def test_layernorm_softmax(bnn):
     assert _rel(s.grad, s32.grad) < 3e-2
 
 
+@pytest.mark.parametrize("rows,c", [(37, 64), (101, 128), (77, 256), (65, 512), (33, 1024), (50, 100), (4099, 768)])
+def test_row_kernels_all_group_shapes(bnn, rows, c):
+    """LayerNorm / softmax row kernels: every (lanes-per-row, vectors-per-lane) instantiation, ragged row counts,
+    and the scalar fallback for rows that are not a multiple of 8 elements."""
+    torch.manual_seed(rows + c)
+    dev = _dev()
+    ln = bnn.LayerNorm(c, eps=1e-5).to(dev)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(rows, c, device=dev).to(BF16).requires_grad_(True)
+    y = ln(x)
+    x32 = x.detach().float().requires_grad_(True)
+    w32, b32 = ln.weight.detach().clone().requires_grad_(True), ln.bias.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(x32, (c,), w32, b32, 1e-5)
+    assert _rel(y, yr) < 1.5e-2
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr.backward(dy.float())
+    assert _rel(x.grad, x32.grad) < 3e-2
+    assert _rel(ln.weight.grad, w32.grad) < 3e-2 and _rel(ln.bias.grad, b32.grad) < 3e-2
+    s = (torch.randn(rows, c, device=dev) * 2).to(BF16).requires_grad_(True)
+    p = bnn.softmax(s, 0.5)
+    s32 = s.detach().float().requires_grad_(True)
+    pr = torch.softmax(s32 * 0.5, -1)
+    assert _rel(p, pr) < 1e-2
+    g = torch.randn_like(p)
+    p.backward(g)
+    pr.backward(g.float())
+    assert _rel(s.grad, s32.grad) < 3e-2
+
+
 # ------------------------------------------------------------------ losses
 def test_softmax_xent_and_mse(F, bnn):
     torch.manual_seed(9)
