@@ -61,6 +61,7 @@ struct GemmParams {
   // strided-batched mode (attention): blockIdx.z = outer * batch_inner + inner; operands come from
   // 4-D tensor maps (col, row, inner, outer); D is offset by outer * d_outer + inner * d_inner elements
   int batched, batch_inner;
+  int batch_count;         // persistent batched mode: number of z slices
   long long d_outer, d_inner;
 };
 
@@ -149,11 +150,12 @@ __device__ __forceinline__ void transform_chunk(const GemmParams& p, int col0, f
 }
 
 template <int NV>
-__device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, int col0, float (&v)[NV], bool vec_ok) {
+__device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, int col0, float (&v)[NV], bool vec_ok,
+                                                size_t d_off = 0) {
   transform_chunk<NV>(p, col0, v);
   const bool full = (col0 + NV <= p.N);
   if (p.out_fp32) {
-    float* d = reinterpret_cast<float*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+    float* d = reinterpret_cast<float*>(p.D) + d_off + static_cast<size_t>(row) * p.ldd + col0;
     if (p.atomic_out) {
       if (full && vec_ok) {
 #pragma unroll
@@ -171,7 +173,7 @@ __device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, in
       _Pragma("unroll") for (int j = 0; j < NV; ++j) if (col0 + j < p.N) d[j] = v[j];
     }
   } else {
-    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + static_cast<size_t>(row) * p.ldd + col0;
+    __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(p.D) + d_off + static_cast<size_t>(row) * p.ldd + col0;
     if (full && vec_ok) {
 #pragma unroll
       for (int j = 0; j < NV; j += 8) {
@@ -403,7 +405,7 @@ constexpr int EPI_WARP_BYTES = 32 * EPI_PITCH;
 
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int q, int m0, int n0,
-                                              uint8_t* stage, bool vec_ok) {
+                                              uint8_t* stage, bool vec_ok, size_t d_off = 0) {
   const int lane = static_cast<int>(lane_id());
   const int row = m0 + q * 32 + lane;
   const int elt = p.out_fp32 ? 4 : 2;
@@ -419,7 +421,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-      store_row_chunk<32>(p, row, col0, v, vec_ok);
+      store_row_chunk<32>(p, row, col0, v, vec_ok, d_off);
     }
     return;
   }
@@ -460,7 +462,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       if (grow < p.M && col < p.N) {
         const uint4 val = *reinterpret_cast<const uint4*>(stage + r * EPI_PITCH + ch * 16);
         *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.D) +
-                                  (static_cast<size_t>(grow) * p.ldd + col) * elt) = val;
+                                  (d_off + static_cast<size_t>(grow) * p.ldd + col) * elt) = val;
       }
     }
     __syncwarp();
@@ -487,7 +489,8 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   const int warp = threadIdx.x >> 5;
   const int tiles_m = (p.M + BM - 1) / BM;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
+  const int tiles_per_z = tiles_m * tiles_n;
+  const int num_tiles = tiles_per_z * (p.batched ? p.batch_count : 1);   // batched: z-major tile list
   const int num_kt = (p.K + BK - 1) / BK;
 
   if (warp == 0 && elect_one()) {
@@ -522,24 +525,41 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         // consecutive CTAs share the same N block (the B tile stays hot in L2) and walk M
-        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
+        const int m0 = (rem % tiles_m) * BM, n0 = (rem / tiles_m) * BN;
+        const int zo = p.batched ? z / p.batch_inner : 0, zi = p.batched ? z % p.batch_inner : 0;
         for (int kt = 0; kt < num_kt; ++kt) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           const int k0 = kt * BK;
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-          if (!p.a_mn) {
-            tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
-          } else {
+          if (p.batched) {
+            if (!p.a_mn) {
+              tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, zi, zo);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[s], m0 + j * 64, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
-          } else {
+              for (int j = 0; j < BM / 64; ++j) tma_load_4d(sa + j * 8192, &tmA, &full_bar[s], m0 + j * 64, k0, zi, zo);
+            }
+            if (!p.b_mn) {
+              tma_load_4d(sb, &tmB, &full_bar[s], k0, n0, zi, zo);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0);
+              for (int j = 0; j < BN / 64; ++j) tma_load_4d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0, zi, zo);
+            }
+          } else {
+            if (!p.a_mn) {
+              tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &tmA, &full_bar[s], m0 + j * 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0);
+            }
           }
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -587,10 +607,15 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
       const int acc = t & 1;
       const uint32_t aph = (t >> 1) & 1;
-      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
+      const int m0 = (rem % tiles_m) * BM, n0 = (rem / tiles_m) * BN;
+      size_t d_off = 0;
+      if (p.batched)
+        d_off = static_cast<size_t>(z / p.batch_inner) * p.d_outer + static_cast<size_t>(z % p.batch_inner) * p.d_inner;
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base + acc * BN, q, m0, n0, epi_stage + q * EPI_WARP_BYTES, vec_ok);
+      epilogue_tile<BN>(p, tmem_base + acc * BN, q, m0, n0, epi_stage + q * EPI_WARP_BYTES,
+                        vec_ok && ((d_off * elt) & 15) == 0, d_off);
       tc_fence_before();
       __syncwarp();
       if (lane_id() == 0) mbar_arrive(&tempty_bar[acc]);
@@ -1204,7 +1229,7 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
   p.tile_flags = tile_flags; p.flag_epoch = flag_epoch; p.alpha = alpha;
   p.flag_elem_off = flag_elem_off; p.flag_tile_elems = flag_tile_elems; p.ldb = ldb;
   p.flag_bias_off = (tile_flags != nullptr && bias != nullptr) ? flag_bias_off : -1;
-  p.batched = 0; p.batch_inner = 1; p.d_outer = 0; p.d_inner = 0;
+  p.batched = 0; p.batch_inner = 1; p.batch_count = 1; p.d_outer = 0; p.d_inner = 0;
   if (p.atomic_out && (!out_fp32 || bias != nullptr || act != 0)) return -3;
   const int max_stages = (bn == 256) ? 4 : (bn == 128 ? 6 : 8);
   p.stages = per < max_stages ? (per < 2 ? 2 : per) : max_stages;
@@ -1226,10 +1251,10 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
     const char* e = std::getenv("BATON_GEMM_2CTA");
     two_cta_on = (e == nullptr) ? 2 : (e[0] == '1' ? 1 : 0);   // unset: automatic, 1: whenever legal, 0: never
   }
-  // measured (profiles/gemm_variants.md): pairs win once the K loop is long enough to amortise the
-  // cluster-scope handshakes (8192^3: 797 us vs 860 us) and lose on short-K BERT shapes (51 vs 31 us)
+  // measured (profiles/r1_gemm_variants.md): with the lean epilogue CTA pairs win on every shape that fills the
+  // machine (8192^3: 767 vs 801 us, BERT qkv 4096x2304x768: 21.9 vs 25.3 us, BERT-base round 521 vs 538 ms)
   const int tiles_2cta = ((M + 2 * BM - 1) / (2 * BM)) * ((N + 255) / 256);
-  const bool two_cta_auto = two_cta_on == 2 && per >= 32 && tiles_2cta >= 2 * 74;
+  const bool two_cta_auto = two_cta_on == 2 && tiles_2cta >= 74;
   if ((two_cta_on == 1 || two_cta_auto) && split_k == 1 && tile_flags == nullptr && bn == 256 && num_tiles >= 148) {
     // CTA pairs: 256 x 256 tiles, each CTA TMA-loads its 128 rows of A and its 128-row half of B
     CUtensorMap tb2;
@@ -1285,6 +1310,23 @@ extern "C" int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int
   p.batched = 1; p.batch_inner = n_inner; p.d_outer = d_outer; p.d_inner = d_inner;
   if (p.atomic_out && !out_fp32) return -3;
   dim3 grid((N + bn - 1) / bn, (M + BM - 1) / BM, n_outer * n_inner);
+  p.batch_count = n_outer * n_inner;
+  // attention-sized batches are thousands of one- or two-k-tile problems: a CTA per problem is all
+  // prologue (TMEM alloc, barrier init, first TMA round trip).  Persistent CTAs amortise that and overlap
+  // the epilogue of problem i with the loads + MMAs of problem i+1.
+  static int batched_persistent = -1;
+  if (batched_persistent < 0) {
+    const char* e = std::getenv("BATON_GEMM_BATCHED_PERSISTENT");
+    batched_persistent = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  const long long total_tiles = static_cast<long long>(grid.x) * grid.y * grid.z;
+  if (batched_persistent && total_tiles >= 2 * 148 && total_tiles < (1ll << 30)) {
+    p.epi_staged = 1;
+    const int nt = static_cast<int>(total_tiles);
+    if (bn == 256) return launch_persistent<256, 4>(ta, tb, p, nt, stream);
+    if (bn == 128) return launch_persistent<128, 6>(ta, tb, p, nt, stream);
+    return launch_persistent<64, 8>(ta, tb, p, nt, stream);
+  }
   if (bn == 256) return launch_fixed<256, 4>(ta, tb, p, grid, stream);
   if (bn == 128) return launch_fixed<128, 6>(ta, tb, p, grid, stream);
   return launch_fixed<64, 8>(ta, tb, p, grid, stream);

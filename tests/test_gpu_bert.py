@@ -18,7 +18,8 @@ def test_attention_core_forward_backward():
     from baton_b200.ops import nn as bnn
     torch.manual_seed(0)
     dev = torch.device("cuda:0")
-    for (B, S, H, dh) in [(4, 128, 12, 64), (2, 64, 2, 64), (3, 256, 4, 32)]:
+    # the last two shapes have >= 296 (batch x head x tile) problems: persistent batched kernel
+    for (B, S, H, dh) in [(4, 128, 12, 64), (2, 64, 2, 64), (3, 256, 4, 32), (32, 128, 12, 64), (8, 256, 12, 64)]:
         D = H * dh
         qkv = (torch.randn(B * S, 3 * D, device=dev) * 0.5).to(BF16).requires_grad_(True)
         out = bnn.attention(qkv, B, S, H, dh)
