@@ -264,11 +264,13 @@ def test_maxpool_avgpool(bnn):
 
 
 # ------------------------------------------------------------------ normalisation
+@pytest.mark.parametrize("n,h,c", [(32, 8, 64), (128, 8, 64), (9, 5, 128), (128, 1, 512), (7, 3, 24), (3, 2, 2048)])
 @pytest.mark.parametrize("relu,with_res", [(False, False), (True, False), (True, True)])
-def test_batchnorm_fwd_bwd(bnn, relu, with_res):
+def test_batchnorm_fwd_bwd(bnn, relu, with_res, n, h, c):
+    """Channel counts cover the vectorised column reductions (C/8 a power of two), ragged row counts, and the
+    scalar fallback (24 channels); 2048 channels = one thread group per row."""
     torch.manual_seed(7)
     dev = _dev()
-    n, h, c = 32, 8, 64
     bn = bnn.BatchNorm2d(c, relu=relu).to(dev)
     with torch.no_grad():
         bn.weight.uniform_(0.5, 1.5)
