@@ -27,13 +27,16 @@ inline T* opt_ptr(const std::optional<at::Tensor>& t) {
 void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::optional<at::Tensor>& bias, int64_t M,
           int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd, bool a_mn, bool b_mn, int64_t act,
           int64_t split_k, bool accumulate, double alpha, const std::optional<at::Tensor>& flags, int64_t flag_epoch,
-          int64_t flag_elem_off, int64_t flag_tile_elems, int64_t flag_bias_off, int64_t force_bn, bool simt) {
+          int64_t flag_elem_off, int64_t flag_tile_elems, int64_t flag_bias_off, int64_t force_bn, bool simt,
+          const std::optional<at::Tensor>& col_stats) {
   CHECK_CUDA(a); CHECK_CUDA(b); CHECK_CUDA(d);
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm operands must be bf16");
   TORCH_CHECK(d.scalar_type() == at::kBFloat16 || d.scalar_type() == at::kFloat, "gemm output must be bf16/fp32");
   const c10::cuda::CUDAGuard guard(a.device());
   const int out_fp32 = d.scalar_type() == at::kFloat;
   const float* bp = opt_ptr<const float>(bias);
+  TORCH_CHECK(!col_stats.has_value() || (!simt && col_stats->scalar_type() == at::kFloat && col_stats->numel() >= 2 * N),
+              "col_stats needs the tensor-core path and a [2N] fp32 buffer");
   if (simt) {
     check(b200_gemm_simt(cptr(a), cptr(b), ptr(d), bp, M, N, K, lda, ldb, ldd, a_mn, b_mn, out_fp32, act, accumulate,
                          static_cast<float>(alpha), cur_stream()),
@@ -43,7 +46,7 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::opt
   check(b200_gemm_bf16(cptr(a), cptr(b), ptr(d), bp, M, N, K, lda, ldb, ldd, a_mn, b_mn, out_fp32, act, split_k,
                        accumulate, static_cast<float>(alpha), opt_ptr<const uint32_t>(flags),
                        static_cast<uint32_t>(flag_epoch), flag_elem_off, static_cast<int>(flag_tile_elems), flag_bias_off,
-                       static_cast<int>(force_bn), cur_stream()),
+                       static_cast<int>(force_bn), opt_ptr<float>(col_stats), cur_stream()),
         "gemm_bf16");
 }
 

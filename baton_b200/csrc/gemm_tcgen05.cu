@@ -46,6 +46,7 @@ struct GemmParams {
   int out_fp32;           // 1: D is fp32, 0: D is bf16
   int act;                // 0 none, 1 relu, 2 gelu(tanh)
   int epi_staged;         // persistent kernels: 1 = smem-staged row-coalesced stores, 0 = direct per-lane stores
+  float* col_stats;       // optional [2N]: += column sums / sums of squares of the (bf16-rounded) output (BatchNorm)
   int a_mn, b_mn;         // operand majors
   int k_tiles_per_split;  // split-K: k tiles handled by one z-slice
   int atomic_out;         // 1: red.add fp32 into D
@@ -105,6 +106,42 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t
 }
 
 // bias + activation + cast + store of `NV` consecutive output columns of one row
+// Column sums of a 32 x 32 register block held one ROW per lane.  Butterfly: at every step a lane keeps one
+// half of its remaining columns and trades the other half with its partner, so after 5 steps (31 shuffles)
+// lane j owns the complete sum of column j.
+#define COLSUM_STEP(OFF, HALF)                                                  \
+  {                                                                             \
+    const bool upper = (lane & (OFF)) != 0;                                     \
+    _Pragma("unroll") for (int i = 0; i < (HALF); ++i) {                        \
+      const float keep = upper ? t[i + (HALF)] : t[i];                          \
+      const float send = upper ? t[i] : t[i + (HALF)];                          \
+      t[i] = keep + __shfl_xor_sync(0xffffffffu, send, (OFF));                  \
+    }                                                                           \
+  }
+__device__ __forceinline__ float warp_colsum32(float (&t)[32]) {
+  const uint32_t lane = lane_id();
+  COLSUM_STEP(16, 16) COLSUM_STEP(8, 8) COLSUM_STEP(4, 4) COLSUM_STEP(2, 2) COLSUM_STEP(1, 1)
+  return t[0];
+}
+#undef COLSUM_STEP
+// BatchNorm batch statistics fused into the producing GEMM: every lane of the warp must call this.  Rows
+// beyond M hold exact zeros (TMA zero-fills out-of-range operand rows; no bias / activation in this mode).
+__device__ __forceinline__ void accumulate_col_stats(const GemmParams& p, int col0, const float (&v)[32]) {
+  float s[32], q[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float r = __bfloat162float(__float2bfloat16_rn(v[j]));   // what the consumer will read back
+    s[j] = r;
+    q[j] = r * r;
+  }
+  const float cs = warp_colsum32(s), cq = warp_colsum32(q);
+  const int col = col0 + static_cast<int>(lane_id());
+  if (col < p.N) {
+    atomicAdd(p.col_stats + col, cs);
+    atomicAdd(p.col_stats + p.N + col, cq);
+  }
+}
+
 // alpha / bias / activation of one row chunk.  The (activation, bias) combination is resolved ONCE per chunk
 // with warp-uniform branches into fully unrolled straight-line code; the per-element runtime switch this
 // replaces cost ~900 SASS instructions per 32-column chunk (ncu: profiles/r1_ncu_gemm_qkv_epilogue.txt).
@@ -345,11 +382,13 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       tmem_ld_wait();
       const int col0 = n0 + c;
-      if (!row_ok || col0 >= p.N) continue;
+      if (col0 >= p.N) continue;                  // warp-uniform
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       transform_chunk<32>(p, col0, v);
+      if (p.col_stats != nullptr) accumulate_col_stats(p, col0, v);
+      if (!row_ok) continue;
       const bool full = (col0 + 32 <= p.N);
       if (p.atomic_out) {
         float* d = reinterpret_cast<float*>(drow) + col0;
@@ -417,10 +456,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       tmem_ld_32x32b_x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       tmem_ld_wait();
       const int col0 = n0 + c;
-      if (row >= p.M || col0 >= p.N) continue;
+      if (col0 >= p.N) continue;                  // warp-uniform
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (p.col_stats != nullptr) accumulate_col_stats(p, col0, v);   // alpha == 1, no bias / act in this mode
+      if (row >= p.M) continue;
       store_row_chunk<32>(p, row, col0, v, vec_ok, d_off);
     }
     return;
@@ -439,6 +480,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       transform_chunk<32>(p, col0, v);
+      if (p.col_stats != nullptr) accumulate_col_stats(p, col0, v);
       if (p.out_fp32) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
@@ -1183,9 +1225,11 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
                               long long lda, long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act,
                               int split_k, int accumulate, float alpha, const uint32_t* tile_flags,
                               uint32_t flag_epoch, long long flag_elem_off, int flag_tile_elems,
-                              long long flag_bias_off, int force_bn, cudaStream_t stream) {
+                              long long flag_bias_off, int force_bn, float* col_stats, cudaStream_t stream) {
   using namespace b200;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  // fused BatchNorm statistics: plain single-pass GEMM only (no split-K partials, no bias / activation / scaling)
+  if (col_stats != nullptr && (split_k != 1 || bias != nullptr || act != 0 || alpha != 1.0f || accumulate)) return -3;
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
     return -2;
   int bn = force_bn > 0 ? force_bn : (N > 128 ? 256 : (N > 64 ? 128 : 64));
@@ -1226,6 +1270,7 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
     epi_staged = (e != nullptr && e[0] == '0') ? 0 : 1;   // default on: BERT-base round 553 -> 538 ms
   }
   p.epi_staged = epi_staged;
+  p.col_stats = col_stats;
   p.tile_flags = tile_flags; p.flag_epoch = flag_epoch; p.alpha = alpha;
   p.flag_elem_off = flag_elem_off; p.flag_tile_elems = flag_tile_elems; p.ldb = ldb;
   p.flag_bias_off = (tile_flags != nullptr && bias != nullptr) ? flag_bias_off : -1;
@@ -1305,6 +1350,7 @@ extern "C" int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int
   p.a_mn = a_mn; p.b_mn = b_mn; p.k_tiles_per_split = (K + BK - 1) / BK; p.cluster_k = 1;
   p.atomic_out = accumulate ? 1 : 0;
   p.epi_staged = 0;
+  p.col_stats = nullptr;
   p.tile_flags = nullptr; p.flag_epoch = 0; p.alpha = alpha; p.flag_elem_off = 0; p.flag_tile_elems = 0;
   p.ldb = ldb; p.flag_bias_off = -1; p.stages = 4;
   p.batched = 1; p.batch_inner = n_inner; p.d_outer = d_outer; p.d_inner = d_inner;

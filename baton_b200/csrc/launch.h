@@ -13,7 +13,7 @@ extern "C" {
 int b200_gemm_bf16(const void* a, const void* b, void* d, const float* bias, int M, int N, int K, long long lda,
                    long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act, int split_k, int accumulate,
                    float alpha, const uint32_t* tile_flags, uint32_t flag_epoch, long long flag_elem_off, int flag_tile_elems,
-                   long long flag_bias_off, int force_bn, cudaStream_t stream);
+                   long long flag_bias_off, int force_bn, float* col_stats, cudaStream_t stream);
 int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int M, int N, int K, long long lda, long long ldb,
                            long long ldd, int a_mn, int b_mn, int out_fp32, int act, float alpha, int n_outer,
                            int n_inner, long long a_outer, long long a_inner, long long b_outer, long long b_inner,

@@ -132,6 +132,15 @@ class ResNet(FederatedModule):
             m.workspace = ws[off: off + 4 * m.num_features]
             off += 4 * m.num_features
         self.stats_workspace = ws
+        # convolution -> BatchNorm pairs: the conv GEMM's epilogue accumulates the batch statistics straight
+        # into the BatchNorm's workspace, so the separate statistics pass over the activation disappears
+        for parent in self.modules():
+            for conv_name, bn_name in (("conv1", "bn1"), ("conv2", "bn2"), ("conv3", "bn3")):
+                conv, bn = getattr(parent, conv_name, None), getattr(parent, bn_name, None)
+                if isinstance(conv, bnn.Conv2d) and isinstance(bn, bnn.BatchNorm2d):
+                    conv.bn_ws = bn.workspace
+            if isinstance(parent, _Downsample):
+                parent[0].bn_ws = parent[1].workspace
         return ws
 
 

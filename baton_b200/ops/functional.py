@@ -73,11 +73,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: Optional[int] = None,
          n_valid: Optional[int] = None, flags: Optional[torch.Tensor] = None, flag_epoch: int = 0,
          flag_elem_off: int = 0, flag_tile_elems: int = 0, flag_bias_off: int = -1, force_bn: int = 0,
-         force_simt: bool = False) -> torch.Tensor:
+         force_simt: bool = False, col_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``out[M,N] = act(alpha * A @ B^T + bias)`` on tcgen05 tensor cores.
 
     ``n_valid`` limits the written columns (used when B carries zero K-padding
-    rows, e.g. the wgrad of a layer whose K was padded to a multiple of 8)."""
+    rows, e.g. the wgrad of a layer whose K was padded to a multiple of 8).
+
+    ``col_stats`` (fp32 ``[2N]``): the epilogue also accumulates the per-column sum and sum of squares of the
+    bf16 output into it -- the BatchNorm batch statistics of a convolution, without a second pass over the
+    activation.  Only legal where :func:`gemm_stats_fusable` says so (single-pass tensor-core GEMM)."""
     C = load()
     M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
@@ -92,10 +96,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     lda, ldb = _pitch(a), _pitch(b)
     use_simt = force_simt or not (_tma_ok(a) and _tma_ok(b))
     if use_simt:
+        assert col_stats is None, "fused column statistics need the tensor-core path"
         C.gemm(a, b, out, bias, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, 1, accumulate, alpha, None, 0, 0, 0, -1, 0,
-               True)
+               True, None)
         return out
     bn = force_bn or pick_bn(M, N)
+    if col_stats is not None:
+        split_k = 1
     if split_k is None:
         if accumulate and out.dtype == torch.float32:
             split_k = pick_split_k(M, N, K, bn)          # atomic split-K straight into the gradient arena
@@ -106,8 +113,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if split_k > 1:
         assert out.dtype == torch.float32 and bias is None and act == 0
     C.gemm(a, b, out, bias, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, split_k, accumulate, alpha, flags, flag_epoch,
-           flag_elem_off, flag_tile_elems, flag_bias_off, bn, False)
+           flag_elem_off, flag_tile_elems, flag_bias_off, bn, False, col_stats)
     return out
+
+
+def gemm_stats_fusable(M: int, N: int, K: int) -> bool:
+    """Would :func:`gemm` run this (K-padded, TMA-legal) problem as ONE pass per output tile?  Cluster split-K
+    keeps partial tiles in several CTAs, so column statistics cannot be taken in its epilogue."""
+    return K % 8 == 0 and pick_cluster_k(M, N, K, pick_bn(M, N)) == 1
 
 
 # ---------------------------------------------------------------------------- elementwise / optimizer

@@ -226,7 +226,7 @@ class Linear(nn.Module):
 # ================================================================================ Conv2d (NHWC, implicit GEMM)
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, w_bf16, kh, kw, stride, pad, anchor):
+    def forward(ctx, x, weight, w_bf16, kh, kw, stride, pad, anchor, stats=None):
         weight = _unwrap(weight)
         n, h, w, c = x.shape
         cout = w_bf16.shape[0]
@@ -238,13 +238,13 @@ class _ConvFn(torch.autograd.Function):
         if ctx.center:
             col, ho, wo, kp = x.view(n, c), 1, 1, c
             wc = w_bf16.view(cout, kh * kw, c)[:, (kh // 2) * kw + kw // 2, :]
-            y = F.gemm(col, wc)
+            y = F.gemm(col, wc, col_stats=stats)
         else:
             if kh == 1 and kw == 1 and stride == 1 and pad == 0 and c % 8 == 0:
                 col, ho, wo, kp = x.view(n * h * w, c), h, w, c
             else:
                 col, ho, wo, kp = F.im2col(x, kh, kw, stride, pad)
-            y = F.gemm(col, w_bf16)
+            y = F.gemm(col, w_bf16, col_stats=stats)
         ctx.save_for_backward(col, w_bf16)
         ctx.weight = weight
         ctx.geom = (n, h, w, c, kh, kw, stride, pad, ho, wo, kp)
@@ -281,7 +281,7 @@ class _ConvFn(torch.autograd.Function):
             if ctx.needs_dx:
                 wc = w_bf16.view(cout, kh * kw, c)[:, tap, :]
                 dx = F.gemm(dy2, wc, b_mn=True).view(n, 1, 1, c)
-            return dx, gw, None, None, None, None, None, None
+            return dx, gw, None, None, None, None, None, None, None
         if tgt is not None:
             # the arena view is channels_last: physical [Cout, KH, KW, Cin] == [Cout, K]
             out2d = tgt.permute(0, 2, 3, 1).reshape(cout, k_true) if tgt.dim() == 4 else tgt.view(cout, k_true)
@@ -298,7 +298,7 @@ class _ConvFn(torch.autograd.Function):
                 dx = dcol.view(n, h, w, c)
             else:
                 dx = F.col2im(dcol, (n, h, w, c), kh, kw, stride, pad, ho, wo)
-        return dx, gw, None, None, None, None, None, None
+        return dx, gw, None, None, None, None, None, None, None
 
 
 class Conv2d(nn.Module):
@@ -329,14 +329,33 @@ class Conv2d(nn.Module):
             return y.permute(0, 2, 3, 1)
         if getattr(self, "fp8", False):
             return conv2d_fp8(x, self)
-        return _ConvFn.apply(x, _wrap(self.weight, x), self._w_bf16(), self.kernel_size, self.kernel_size,
-                             self.stride, self.padding, _anchor(x, self.weight))
+        stats = self._fusable_stats(x)
+        y = _ConvFn.apply(x, _wrap(self.weight, x), self._w_bf16(), self.kernel_size, self.kernel_size,
+                          self.stride, self.padding, _anchor(x, self.weight), stats)
+        if stats is not None:
+            y._bn_stats_ws = stats      # tells the BatchNorm that owns this workspace to skip its statistics pass
+        return y
+
+    def _fusable_stats(self, x):
+        """The following BatchNorm's statistics workspace (``bn_ws``, linked by the model) if this call's GEMM
+        can accumulate the batch statistics in its epilogue; ``None`` otherwise."""
+        ws = getattr(self, "bn_ws", None)
+        if ws is None or not self.training or not torch.is_grad_enabled():
+            return None
+        n, h, w, c = x.shape
+        k, s_, p_ = self.kernel_size, self.stride, self.padding
+        ho, wo = (h + 2 * p_ - k) // s_ + 1, (w + 2 * p_ - k) // s_ + 1
+        centre = h == 1 and w == 1 and k % 2 == 1 and p_ == k // 2 and c % 8 == 0 and k > 1
+        kdim = c if (centre or (k == 1 and c % 8 == 0)) else F.round_up(k * k * c, 8)
+        cout = self.weight.shape[0]
+        return ws[: 2 * cout] if F.gemm_stats_fusable(n * ho * wo, cout, kdim) else None
 
 
 # ================================================================================ BatchNorm (+residual +ReLU)
 class _BNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, rmean, rvar, nbt, eps, momentum, relu, training, ws, anchor):
+    def forward(ctx, x, residual, gamma, beta, rmean, rvar, nbt, eps, momentum, relu, training, ws, anchor,
+                stats_ready=False):
         gamma, beta = _unwrap(gamma), _unwrap(beta)
         C_ = load()
         c = x.shape[-1]
@@ -347,7 +366,7 @@ class _BNFn(torch.autograd.Function):
         sums_f, sums_b = ws[: 2 * c], ws[2 * c:]
         save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
         save_rstd = torch.empty(c, dtype=torch.float32, device=x.device)
-        if training:
+        if training and not stats_ready:     # stats_ready: the producing GEMM's epilogue already accumulated them
             C_.bn_stats(x, sums_f, rows, c)
         C_.bn_apply(x, residual, y, sums_f, gamma, beta, rmean, rvar, save_mean, save_rstd, nbt, rows, c, eps,
                     momentum, relu, training)
@@ -375,7 +394,7 @@ class _BNFn(torch.autograd.Function):
         C_.bn_bwd_apply(x, y, dy, dx, dres, gamma, mean, rstd, ctx.sums_b, tg, tb, ctx.rows, ctx.c, ctx.relu)
         if ctx.has_res and dres is None:
             dres = dy
-        return dx, dres, gg, gb, None, None, None, None, None, None, None, None, None
+        return dx, dres, gg, gb, None, None, None, None, None, None, None, None, None, None
 
 
 class BatchNorm2d(nn.Module):
@@ -405,9 +424,12 @@ class BatchNorm2d(nn.Module):
         ws = self.workspace
         if ws is None:
             ws = torch.zeros(4 * self.num_features, dtype=torch.float32, device=x.device)
+        fused = getattr(x, "_bn_stats_ws", None)      # set by the producing Conv2d when its GEMM took the statistics
+        ready = (fused is not None and self.workspace is not None and self.training
+                 and fused.data_ptr() == self.workspace.data_ptr())
         return _BNFn.apply(x, residual, _wrap(self.weight, x), _wrap(self.bias, x), self.running_mean,
                            self.running_var, self.num_batches_tracked if self.training else None, self.eps,
-                           self.momentum, self.relu, self.training, ws, _anchor(x, self.weight))
+                           self.momentum, self.relu, self.training, ws, _anchor(x, self.weight), ready)
 
 
 # ================================================================================ pooling / misc

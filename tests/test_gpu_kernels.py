@@ -149,6 +149,51 @@ def test_gemm_two_cta_pairs(F, a_mn, b_mn):
     assert _rel(out2, torch.relu(ref + bias)) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(8192, 64, 576), (32768, 64, 152), (1000, 72, 64), (32768, 256, 64), (32768, 128, 128),
+                                   (20000, 256, 192)])
+def test_gemm_fused_column_statistics(F, M, N, K):
+    """BatchNorm statistics taken in the GEMM epilogue (fixed, persistent and CTA-pair kernels): column sums and
+    sums of squares of the bf16 output, ragged M / N included."""
+    torch.manual_seed(M + N + K)
+    dev = _dev()
+    A = torch.randn(M, K, device=dev).to(BF16)
+    B = (torch.randn(N, K, device=dev) * 0.2).to(BF16)
+    assert F.gemm_stats_fusable(M, N, K)
+    stats = torch.zeros(2 * N, device=dev)
+    out = F.gemm(A, B, col_stats=stats)
+    ref = F.gemm(A, B)
+    assert torch.equal(out, ref)
+    o = out.float()
+    assert _rel(stats[:N], o.sum(0)) < 2e-3, _rel(stats[:N], o.sum(0))
+    assert _rel(stats[N:], (o * o).sum(0)) < 2e-3
+    F.gemm(A, B, col_stats=stats)                        # accumulates
+    assert _rel(stats[N:], 2 * (o * o).sum(0)) < 2e-3
+
+
+def test_conv_bn_fused_statistics_match_separate_pass(bnn):
+    torch.manual_seed(3)
+    dev = _dev()
+    x = torch.randn(128, 8, 8, 64, device=dev).to(BF16)
+    outs = []
+    for fused in (False, True):
+        torch.manual_seed(4)
+        conv = bnn.Conv2d(64, 64, 3, 1, 1).to(dev)
+        bn = bnn.BatchNorm2d(64, relu=True).to(dev)
+        bn.workspace = torch.zeros(4 * 64, device=dev)
+        if fused:
+            conv.bn_ws = bn.workspace
+        h = conv(x)
+        assert (getattr(h, "_bn_stats_ws", None) is not None) == fused
+        y = bn(h)
+        y.float().sum().backward()
+        outs.append((y.detach().clone(), bn.running_mean.clone(), bn.running_var.clone(), bn.workspace[:128].clone(),
+                     conv.weight.grad.clone()))
+    (y0, m0, v0, s0, g0), (y1, m1, v1, s1, g1) = outs
+    assert _rel(s1, s0) < 1e-3
+    assert _rel(y1, y0) < 1e-2 and torch.allclose(m0, m1, atol=1e-4) and torch.allclose(v0, v1, rtol=1e-3, atol=1e-4)
+    assert _rel(g1, g0) < 2e-2
+
+
 def test_gemm_simt_fallback_small_pitch(F):
     torch.manual_seed(2)
     dev = _dev()
