@@ -864,6 +864,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* cstat = reinterpret_cast<float*>(tmem_slot + 4);   // [2 * BN] column statistics of this CTA's rows
 
   griddep_launch_dependents();  // PDL: the next kernel may start its prologue now
   const int warp = threadIdx.x >> 5;
@@ -1014,6 +1015,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int t = threadIdx.x - 128;             // 0..127
       const size_t elt = p.out_fp32 ? 4 : 2;
       const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * elt) % 16 == 0);
+      const bool want_stats = p.col_stats != nullptr;
+      if (want_stats) {
+        for (int i = t; i < 2 * BN; i += 128) cstat[i] = 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+      }
+      // 128 % CG == 0: a thread always lands on the same 8 columns, so its statistics stay in registers
+      float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int item = t; item < rows_per * CG; item += 128) {
         const int lrow = static_cast<int>(me) * rows_per + item / CG;
         const int c = (item % CG) * 8;
@@ -1025,7 +1033,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
         }
         const int row = m0 + lrow, col0 = n0 + c;
+        if (want_stats) {                          // rows >= M are exact zeros (TMA zero fill)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float rnd = __bfloat162float(__float2bfloat16_rn(v[j]));
+            cs[j] += rnd;
+            cq[j] = fmaf(rnd, rnd, cq[j]);
+          }
+        }
         if (row < p.M && col0 < p.N) store_row_chunk<8>(p, row, col0, v, vec_ok);
+      }
+      if (want_stats) {
+        if (t < rows_per * CG) {
+          const int c = (t % CG) * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            atomicAdd(cstat + c + j, cs[j]);
+            atomicAdd(cstat + BN + c + j, cq[j]);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = t; i < BN; i += 128)
+          if (n0 + i < p.N) {
+            atomicAdd(p.col_stats + n0 + i, cstat[i]);
+            atomicAdd(p.col_stats + p.N + n0 + i, cstat[BN + i]);
+          }
       }
     }
     cluster_sync_all();  // nobody leaves (and frees its smem) while a peer may still read it
@@ -1161,10 +1193,10 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
                       cudaStream_t stream) {
   using L = SmemLayout<BN>;
   constexpr int max_stages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  constexpr int max_smem = max_stages * L::STAGE_BYTES + (2 * MAX_STAGES + 1) * 8 + 16 + 1024;
+  constexpr int max_smem = max_stages * L::STAGE_BYTES + (2 * MAX_STAGES + 1) * 8 + 16 + 2 * BN * 4 + 1024;
   static bool configured = false;
   if (!configured) {
-    const int cap = max_smem > L::PART_BYTES + 2048 ? max_smem : L::PART_BYTES + 2048;
+    const int cap = max_smem > L::PART_BYTES + 4096 ? max_smem : L::PART_BYTES + 4096;
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess)
@@ -1174,7 +1206,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   }
   int ring = p.stages * L::STAGE_BYTES;
   if (p.cluster_k > 1 && L::PART_BYTES > ring) ring = L::PART_BYTES;
-  int smem = ring + (2 * MAX_STAGES + 1) * 8 + 16 + 1024;
+  int smem = ring + (2 * MAX_STAGES + 1) * 8 + 16 + 2 * BN * 4 + 1024;
   // occupancy cap: CTAs of this kernel per SM (shared memory is the limiter we control)
   static int max_ctas = -1;
   if (max_ctas < 0) {
@@ -1229,7 +1261,7 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
   using namespace b200;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   // fused BatchNorm statistics: plain single-pass GEMM only (no split-K partials, no bias / activation / scaling)
-  if (col_stats != nullptr && (split_k != 1 || bias != nullptr || act != 0 || alpha != 1.0f || accumulate)) return -3;
+  if (col_stats != nullptr && (split_k > 1 || bias != nullptr || act != 0 || alpha != 1.0f || accumulate)) return -3;
   if ((lda % 8) || (ldb % 8) || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
     return -2;
   int bn = force_bn > 0 ? force_bn : (N > 128 ? 256 : (N > 64 ? 128 : 64));

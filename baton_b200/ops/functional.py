@@ -102,7 +102,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         return out
     bn = force_bn or pick_bn(M, N)
     if col_stats is not None:
-        split_k = 1
+        assert not accumulate and bias is None and act == 0 and alpha == 1.0
     if split_k is None:
         if accumulate and out.dtype == torch.float32:
             split_k = pick_split_k(M, N, K, bn)          # atomic split-K straight into the gradient arena
@@ -118,9 +118,10 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
 
 
 def gemm_stats_fusable(M: int, N: int, K: int) -> bool:
-    """Would :func:`gemm` run this (K-padded, TMA-legal) problem as ONE pass per output tile?  Cluster split-K
-    keeps partial tiles in several CTAs, so column statistics cannot be taken in its epilogue."""
-    return K % 8 == 0 and pick_cluster_k(M, N, K, pick_bn(M, N)) == 1
+    """Can :func:`gemm` take column statistics of this problem in its epilogue?  Every bf16-output tensor-core
+    path can: single-pass tiles do it from the TMEM rows (butterfly column sums), cluster split-K in the DSMEM
+    reduction; only operands that fall back to the SIMT kernel (pitch not a multiple of 8) cannot."""
+    return K % 8 == 0
 
 
 # ---------------------------------------------------------------------------- elementwise / optimizer

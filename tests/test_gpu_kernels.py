@@ -150,10 +150,10 @@ def test_gemm_two_cta_pairs(F, a_mn, b_mn):
 
 
 @pytest.mark.parametrize("M,N,K", [(8192, 64, 576), (32768, 64, 152), (1000, 72, 64), (32768, 256, 64), (32768, 128, 128),
-                                   (20000, 256, 192)])
+                                   (20000, 256, 192), (2048, 128, 1152), (512, 256, 2304), (500, 200, 4608)])
 def test_gemm_fused_column_statistics(F, M, N, K):
-    """BatchNorm statistics taken in the GEMM epilogue (fixed, persistent and CTA-pair kernels): column sums and
-    sums of squares of the bf16 output, ragged M / N included."""
+    """BatchNorm statistics taken in the GEMM epilogue (fixed, persistent, CTA-pair and cluster split-K kernels):
+    column sums and sums of squares of the bf16 output, ragged M / N included."""
     torch.manual_seed(M + N + K)
     dev = _dev()
     A = torch.randn(M, K, device=dev).to(BF16)
