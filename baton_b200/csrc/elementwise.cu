@@ -204,6 +204,51 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
   }
 }
 
+// 16-byte version (cols % 8 == 0): block = 32 column groups (256 columns) x 8 row lanes, 4 rows in flight per
+// thread; grid.x over column chunks, grid.y over row chunks
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const uint4* __restrict__ x, float* __restrict__ out, long long rows, int cols8, int rows_per_cta) {
+  griddep_launch_dependents();
+  griddep_wait();
+  __shared__ float s[8][32][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int cg = blockIdx.x * 32 + tx;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > rows) r1 = rows;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (cg < cols8) {
+    for (long long r = r0 + ty; r < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r + 8 * u < r1) v[u] = __ldcs(x + (r + 8 * u) * cols8 + cg);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (r + 8 * u < r1) {
+          const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(w[j]);
+            a[2 * j] += f.x;
+            a[2 * j + 1] += f.y;
+          }
+        }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[ty][tx][j] = a[j];
+  __syncthreads();
+  // 256 threads -> 256 columns of this chunk
+  const int col = threadIdx.x, g = col >> 3, j = col & 7;
+  if (blockIdx.x * 32 + g < cols8) {
+    float t = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += s[y][g][j];
+    atomicAdd(out + (static_cast<long long>(blockIdx.x) * 32 + g) * 8 + j, t);
+  }
+}
+
 // ------------------------------------------------------------------ small bf16 elementwise ops
 __global__ void __launch_bounds__(EW_THREADS)
 add_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, long long nv, int relu) {
@@ -268,6 +313,41 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * gelu_grad_f(__bfloat162float(x[i])));
+}
+// 16-byte versions (n % 8 == 0, aligned): 8 elements per thread, streaming loads
+__global__ void __launch_bounds__(EW_THREADS)
+gelu_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long nv) {
+  griddep_launch_dependents();
+  griddep_wait();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 u = __ldcs(x + i);
+    const uint32_t in[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 v = unpack_bf16x2(in[j]);
+      o[j] = pack_bf16x2(gelu_f(v.x), gelu_f(v.y));
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+__global__ void __launch_bounds__(EW_THREADS)
+gelu_bwd_vec_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx, long long nv) {
+  griddep_launch_dependents();
+  griddep_wait();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 u = __ldcs(x + i), g = __ldcs(dy + i);
+    const uint32_t xs[4] = {u.x, u.y, u.z, u.w}, gs[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 v = unpack_bf16x2(xs[j]), d = unpack_bf16x2(gs[j]);
+      o[j] = pack_bf16x2(d.x * gelu_grad_f(v.x), d.y * gelu_grad_f(v.y));
+    }
+    dx[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
 }
 // dst[r, 0:kp] = src[r, 0:k] zero padded (weights whose K is not a multiple of 8, e.g. 7x7x3 = 147)
 __global__ void __launch_bounds__(EW_THREADS)
@@ -355,6 +435,19 @@ extern "C" int b200_gather_rows_i64(const long long* src, const long long* idx, 
 extern "C" int b200_colsum(const void* x, float* out, long long rows, int cols, int accumulate, cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return 0;
   if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * cols, stream);
+  if (cols % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int cols8 = cols / 8;
+    const unsigned gx = static_cast<unsigned>((cols8 + 31) / 32);
+    // ~2 waves of CTAs over the machine, at least one 32-row pass each
+    long long want = (2 * 148 + gx - 1) / gx;
+    long long rpc = (rows + want - 1) / want;
+    rpc = (rpc + 31) / 32 * 32;
+    if (rpc < 32) rpc = 32;
+    dim3 gridv(gx, static_cast<unsigned>((rows + rpc - 1) / rpc));
+    launch_pdl(colsum_vec_kernel, gridv, 256, 0, stream, reinterpret_cast<const uint4*>(x), out, rows, cols8,
+               static_cast<int>(rpc));
+    RET_LAST();
+  }
   long long gy = (rows + 63) / 64;
   if (gy > 64) gy = 64;
   dim3 grid((cols + 31) / 32, static_cast<unsigned>(gy));
@@ -379,12 +472,22 @@ extern "C" int b200_relu_bwd_bf16(const void* y, const void* dy, void* dx, long 
 }
 extern "C" int b200_gelu_bf16(const void* x, void* y, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
+  if (n % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    launch_pdl(gelu_vec_kernel, ew_grid(n / 8), EW_THREADS, 0, stream, reinterpret_cast<const uint4*>(x),
+               reinterpret_cast<uint4*>(y), n / 8);
+    RET_LAST();
+  }
   launch_pdl(gelu_kernel, ew_grid(n), EW_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x),
                                                      reinterpret_cast<__nv_bfloat16*>(y), n);
   RET_LAST();
 }
 extern "C" int b200_gelu_bwd_bf16(const void* x, const void* dy, void* dx, long long n, cudaStream_t stream) {
   if (n <= 0) return 0;
+  if (n % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+    launch_pdl(gelu_bwd_vec_kernel, ew_grid(n / 8), EW_THREADS, 0, stream, reinterpret_cast<const uint4*>(x),
+               reinterpret_cast<const uint4*>(dy), reinterpret_cast<uint4*>(dx), n / 8);
+    RET_LAST();
+  }
   launch_pdl(gelu_bwd_kernel, ew_grid(n), EW_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(x),
                                                          reinterpret_cast<const __nv_bfloat16*>(dy),
                                                          reinterpret_cast<__nv_bfloat16*>(dx), n);

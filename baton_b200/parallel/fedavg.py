@@ -73,6 +73,37 @@ class FedAvgSession:
         # GEMM that is launched right behind it on the compute stream
         self.stream = torch.cuda.Stream(device=self.device, priority=-1) if self.device.type == "cuda" else None
         self.symm.barrier()
+        self.nvls_choice = "forced" if nvls != "auto" else "default"
+        if nvls == "auto" and self.use_nvls and self.delta and self.world > 1 and arena.global_w is not None:
+            self.autotune_nvls()
+
+    def autotune_nvls(self, iters: int = 3) -> None:
+        """Measure, don't guess: time the collective both ways (peer loads/stores vs in-switch
+        ``multimem`` reduce + multicast store) on THIS box and world size and keep the faster one.  Runs on
+        zero deltas (``theta == global`` right after the arena is built), so it leaves the model untouched;
+        every rank takes the max over ranks, so all ranks agree."""
+        import torch.distributed as dist
+        if not torch.equal(self.arena.theta[: self.arena.n_param], self.arena.global_w[: self.arena.n_param]):
+            return                                   # replicas already drifted: keep the default
+        best = {}
+        for mode in (False, True):
+            self.use_nvls = mode
+            ts = []
+            for it in range(iters + 1):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                self.aggregate(my_n=1.0)
+                e1.record()
+                torch.cuda.synchronize(self.device)
+                if it:
+                    ts.append(e0.elapsed_time(e1))
+            best[mode] = min(ts)
+        t = torch.tensor([best[False], best[True]], device=self.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        self.use_nvls = bool(t[1] < t[0])
+        self.nvls_choice = "autotuned p2p {:.0f} us vs nvls {:.0f} us".format(float(t[0]) * 1e3, float(t[1]) * 1e3)
+        self.check()
+        self.symm.barrier()
 
     # ------------------------------------------------------------------ the collective
     def aggregate(self, n_samples_by_rank: Optional[Sequence[float]] = None,

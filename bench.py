@@ -278,6 +278,7 @@ def main(argv=None):
                        "local_epochs": args.local_epochs, "parallelism": "fedavg dp{}".format(world),
                        "backend": args.backend, "wire_dtype": args.wire, "upload": "delta",
                        "nvls": bool(getattr(eng.session, "use_nvls", False)),
+                       "nvls_choice": getattr(eng.session, "nvls_choice", None),
                        "cuda_graph": not args.no_graph, "optimizer": "sgd(lr={}, momentum={})".format(args.lr, args.momentum),
                        "l2": "256 MiB memset between rounds (flush)", "dirichlet_alpha": args.alpha,
                        "logical_clients": n_logical, "sampled_per_round": args.sample_k or n_logical},

@@ -92,6 +92,10 @@ async def test_manager_restart_worker_reregisters_and_resume_from_checkpoint(tmp
         w = await fed.add_worker(n=5, seed=3)
         await fed.get("start_round?n_epoch=2")
         await fed.wait_round_closed()
+        for _ in range(500):                      # the checkpoint is written right AFTER the round lock is released
+            if exp.last_checkpoint:
+                break
+            await asyncio.sleep(0.01)
         path = exp.last_checkpoint
         assert path and path.endswith("lineartest_00001.pt")
         payload = torch.load(path, weights_only=True)

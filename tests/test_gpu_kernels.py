@@ -256,6 +256,18 @@ def test_weighted_sum_cast_gather_colsum(F):
     out = torch.zeros(70, device=dev)
     F.colsum_(m, out)
     assert _rel(out, m.float().sum(0)) < 1e-3
+    for rows, cols in ((3000, 72), (16384, 768), (33, 3072), (5000, 264)):     # 16-byte path, ragged chunks
+        m = torch.randn(rows, cols, device=dev).to(BF16)
+        out = torch.ones(cols, device=dev)
+        F.colsum_(m, out)
+        assert _rel(out, m.float().sum(0) + 1.0) < 1e-3, (rows, cols)
+    for n in (5000, 4096, 8 * 1000 + 8):                                        # scalar and 16-byte GELU paths
+        xv, gv = torch.randn(n, device=dev).to(BF16), torch.randn(n, device=dev).to(BF16)
+        xr2 = xv.float().requires_grad_(True)
+        yr2 = torch.nn.functional.gelu(xr2, approximate="tanh")
+        assert _rel(F.gelu(xv), yr2) < 1e-2
+        yr2.backward(gv.float())
+        assert _rel(F.gelu_bwd(xv, gv), xr2.grad) < 2e-2
     a, b = torch.randn(4096, device=dev).to(BF16), torch.randn(4096, device=dev).to(BF16)
     assert torch.equal(F.add(a, b, relu=True), torch.relu(a.float() + b.float()).to(BF16))
     assert torch.equal(F.relu_bwd(a, b), torch.where(a > 0, b, torch.zeros_like(b)))
