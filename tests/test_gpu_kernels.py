@@ -352,11 +352,16 @@ def test_batchnorm_fwd_bwd(bnn, relu, with_res, n, h, c):
     dy = torch.randn_like(y)
     y.backward(dy)
     yr.backward(dy.float().permute(0, 3, 1, 2))
-    assert _rel(x.grad, x32.grad.permute(0, 2, 3, 1)) < 3e-2
+    # an output within rounding distance of the ReLU kink may land on the other side of it (bf16 output, fp32
+    # atomics in the statistics): such an element's gradient is legitimately dy instead of 0 -- compare away
+    # from the kink
+    pre = yr.detach().permute(0, 2, 3, 1)
+    clear = (pre.abs() > 2e-2).float() if relu else torch.ones_like(pre)
+    assert _rel(x.grad.float() * clear, x32.grad.permute(0, 2, 3, 1) * clear) < 3e-2
     assert _rel(bn.weight.grad, ref.weight.grad) < 3e-2
     assert _rel(bn.bias.grad, ref.bias.grad) < 3e-2
     if with_res:
-        assert _rel(res.grad, r32.grad.permute(0, 2, 3, 1)) < 1e-2
+        assert _rel(res.grad.float() * clear, r32.grad.permute(0, 2, 3, 1) * clear) < 1e-2
 
 
 def test_layernorm_softmax(bnn):
