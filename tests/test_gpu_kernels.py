@@ -343,6 +343,7 @@ def test_batchnorm_fwd_bwd(bnn, relu, with_res, n, h, c):
     if with_res:
         r32 = res.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
         yr = yr + r32
+    pre_act = yr.detach()
     if relu:
         yr = torch.relu(yr)
     assert _rel(y, yr.permute(0, 2, 3, 1)) < 1.5e-2
@@ -355,7 +356,7 @@ def test_batchnorm_fwd_bwd(bnn, relu, with_res, n, h, c):
     # an output within rounding distance of the ReLU kink may land on the other side of it (bf16 output, fp32
     # atomics in the statistics): such an element's gradient is legitimately dy instead of 0 -- compare away
     # from the kink
-    pre = yr.detach().permute(0, 2, 3, 1)
+    pre = pre_act.permute(0, 2, 3, 1)
     clear = (pre.abs() > 2e-2).float() if relu else torch.ones_like(pre)
     assert _rel(x.grad.float() * clear, x32.grad.permute(0, 2, 3, 1) * clear) < 3e-2
     assert _rel(bn.weight.grad, ref.weight.grad) < 3e-2
