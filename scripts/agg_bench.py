@@ -31,8 +31,12 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rows = []
     ctas_list = [int(x) for x in os.environ.get("AGG_CTAS", "148").split(",")]
+    models = os.environ.get("AGG_MODELS", ",".join(SIZES)).split(",")
+    wires = os.environ.get("AGG_WIRES", "bf16,fp32,fp8").split(",")
     for name, n in SIZES.items():
-        for wire in ("bf16", "fp32", "fp8"):
+        if name not in models:
+            continue
+        for wire in wires:
             variants = [("nccl", None, 0)] if wire != "fp8" else []      # NCCL has no block-scaled wire
             for c in ctas_list:
                 variants += [("fused-p2p", False, c)] + ([("fused-nvls", True, c)] if wire != "fp8" else [])
