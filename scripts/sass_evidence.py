@@ -17,24 +17,34 @@ os.makedirs(OUT, exist_ok=True)
 lines = ["# SASS evidence per kernel (`cuobjdump -sass`, sm_100a)", "",
          "`UTCHMMA` = tcgen05.mma kind::f16, `UTCBAR` = tcgen05.commit, `LDTM` = tcgen05.ld, `UTMALDG` = TMA tiled",
          "load, `SYNCS.*` = mbarrier, `LDGMC` = multimem.ld_reduce (NVLS in-switch reduction), `UCGABAR` = cluster",
-         "barrier, `*.SYS` = system-scope (cross-GPU) loads/stores.  Full listings: `gemm_tcgen05.sass`,",
+         "barrier, `*.SYS` = system-scope (cross-GPU) loads/stores, `UTCHMMA.2CTA` / `UTCBAR.2CTA.MULTICAST` = cta_group::2",
+         "MMA and its multicast commit, `UTCQMMA` = block-scaled (MXFP8) MMA, `UTCCP` = tcgen05.cp (scale factors",
+         "into TMEM).  Full listings of the headline instantiations: `gemm_tcgen05.sass`, `gemm_fp8.sass`,",
          "`fedavg.sass`.", ""]
-for f in ["gemm_tcgen05", "fedavg", "elementwise", "conv", "norm", "loss", "gemm_simt"]:
+# full listings only for the headline instantiations (the complete objects are > 10 MB of text)
+FULL = {"gemm_tcgen05": ("gemm_bf16_2cta_kernelILi256", "gemm_bf16_persistent_kernelILi256", "gemm_bf16_fixed_kernelILi256",
+                         "gemm_bf16_tcgen05_kernelILi256ELb1"),
+        "fedavg": ("fedavg_allreduce_kernelILi1", "fedavg_allreduce_kernelILi2"),
+        "gemm_fp8": ("gemm_fp8_kernelILi128",)}
+for f in ["gemm_tcgen05", "gemm_fp8", "quant", "fedavg", "elementwise", "conv", "norm", "loss", "gemm_simt"]:
     obj = os.path.join(BUILD, f + ".o")
     if not os.path.exists(obj):
         continue
     txt = subprocess.run(["cuobjdump", "-sass", obj], stdout=subprocess.PIPE, text=True).stdout
-    if f in ("gemm_tcgen05", "fedavg"):
-        open(os.path.join(OUT, f + ".sass"), "w").write(txt)
     lines.append("## {}.cu".format(f))
+    full = []
     for fn in re.split(r"\n\s*Function : ", txt)[1:]:
         name = fn.split("\n", 1)[0].strip()
-        n_instr = len(re.findall(r"/\*[0-9a-f]{4}\*/", fn))
+        if any(k in name for k in FULL.get(f, ())):
+            full.append("\tFunction : " + fn)
+        n_instr = len(re.findall(r"/\*[0-9a-f]{4,6}\*/", fn))
         c = collections.Counter(m.group(1) for m in KEY.finditer(fn))
         demangled = subprocess.run(["c++filt", name], stdout=subprocess.PIPE, text=True).stdout.strip()
         lines.append("- `{}` ({} instructions)".format(demangled[:120], n_instr))
         if c:
             lines.append("    " + ", ".join("{} x{}".format(k, v) for k, v in sorted(c.items())))
+    if full:
+        open(os.path.join(OUT, f + ".sass"), "w").write("\n".join(full))
     lines.append("")
 open(os.path.join(OUT, "MNEMONICS.md"), "w").write("\n".join(lines))
 print("wrote", OUT)
