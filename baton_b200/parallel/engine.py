@@ -26,7 +26,7 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 import torch
 
 from ..metrics import phase
-from ..train import GraphedLocalSGD
+from ..train import GraphedLocalSGD, PortableLocalSGD
 from .arena import ParamArena
 from .fedavg import FedAvgSession, NcclSession
 
@@ -52,8 +52,16 @@ class FederatedEngine:
         self.arena = ParamArena(model, self.device, momentum=momentum > 0)
         if hasattr(model, "build_workspace"):
             model.build_workspace(self.device)
-        self.trainer = GraphedLocalSGD(model, self.arena, loss=loss, use_graph=use_graph)
-        model._graphed_trainer = self.trainer
+        if self.device.type == "cuda":
+            self.trainer = GraphedLocalSGD(model, self.arena, loss=loss, use_graph=use_graph)
+            model._graphed_trainer = self.trainer
+        else:
+            # CPU / gloo: the plumbing configuration -- same engine, portable PyTorch training loop, and the
+            # torch.distributed session (the fused collective needs NVLink peer memory)
+            if backend == "fused":
+                raise ValueError("backend='fused' needs CUDA devices; use backend='nccl' (torch.distributed, "
+                                 "gloo on CPU) for CPU runs")
+            self.trainer = PortableLocalSGD(model, self.arena, loss=loss)
         Session = {"fused": FedAvgSession, "nccl": NcclSession}[backend]
         self.session = Session(self.arena, group, wire_dtype=wire_dtype, mode=mode, n_ctas=n_ctas, nvls=nvls,
                                tile_flags=tile_flags)

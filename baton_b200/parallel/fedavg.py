@@ -246,13 +246,15 @@ class NcclSession:
         self.wire.copy_((src * w).to(self.wire_dtype))
         if self.world > 1:
             dist.all_reduce(self.wire, group=self.group)
+        # every rank joins the loss reduce every round -- a rank that hosts no sampled client this round
+        # contributes zeros (weight 0); skipping the call there would desynchronise the collectives
+        self.loss_buf.zero_()
         if loss_history is not None:
             k = min(len(loss_history), MAX_LOSS)
-            self.loss_buf.zero_()
             self.loss_buf[:k] = torch.tensor([float(x) for x in loss_history[:k]], device=self.device) * w
-            if self.world > 1:
-                dist.all_reduce(self.loss_buf, group=self.group)
-            self.loss_out.copy_(self.loss_buf)
+        if self.world > 1:
+            dist.all_reduce(self.loss_buf, group=self.group)
+        self.loss_out.copy_(self.loss_buf)
         if self.delta:
             a.global_w.add_(self.wire.float())
         else:

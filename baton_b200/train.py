@@ -216,3 +216,54 @@ class GraphedLocalSGD:
         host = epoch_losses.tolist()          # the ONLY host read of the round
         self.last_stats = {"accuracy": [h[1] / n for h in host], "steps_per_epoch": steps}
         return [h[0] / steps for h in host]
+
+
+class PortableLocalSGD:
+    """Same interface as :class:`GraphedLocalSGD` on plain PyTorch ops -- CPU / gloo runs of the SPMD engine
+    (plumbing config, host-side logic tests).  Parameters stay views of the arena, so the session's reduce and
+    broadcast work unchanged."""
+
+    def __init__(self, model: nn.Module, arena, *, loss: str = "ce", **_unused):
+        self.model, self.arena = model, arena
+        self.loss_kind = loss
+        self.device = arena.device
+        self.last_steps = 1
+        self.kernels_per_epoch = 0
+        self.n_kernels_per_step = 0
+        self.last_stats = {}
+
+    def run(self, X, y, n_epoch: int = 1, lr: float = 0.001, batch_size: int = 32, momentum: float = 0.0,
+            weight_decay: float = 0.0, reshuffle_each_epoch: bool = False, return_device: bool = False, **_ignored):
+        criterion = _loss_fn(self.loss_kind)
+        n = X.shape[0]
+        batch_size = min(batch_size, n)
+        nn.Module.train(self.model, True)
+        opt = torch.optim.SGD(self.model.parameters(), lr=lr, momentum=momentum, weight_decay=weight_decay)
+        perm = torch.randperm(n)
+        out = torch.zeros(n_epoch, 2, dtype=torch.float32)
+        steps = 1
+        for e in range(n_epoch):
+            if reshuffle_each_epoch and e > 0:
+                perm = torch.randperm(n)
+            batches = torch.split(perm, batch_size)
+            steps = len(batches)
+            for idx in batches:
+                opt.zero_grad(set_to_none=True)
+                pred = self.model(X[idx])
+                tgt = y[idx]
+                if pred.shape != tgt.shape and tgt.dtype.is_floating_point:
+                    tgt = tgt.reshape(pred.shape)
+                loss = criterion(pred.float() if tgt.dtype.is_floating_point else pred, tgt)
+                loss.backward()
+                opt.step()
+                out[e, 0] += float(loss.detach())
+                if not tgt.dtype.is_floating_point:
+                    out[e, 1] += float((pred.argmax(-1) == tgt).sum())
+        self.last_steps = steps
+        if self.arena.theta_bf16 is not None:
+            self.arena.sync_shadow()
+        if return_device:
+            return out
+        host = out.tolist()
+        self.last_stats = {"accuracy": [h[1] / n for h in host], "steps_per_epoch": steps}
+        return [h[0] / steps for h in host]
