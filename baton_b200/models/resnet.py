@@ -88,6 +88,7 @@ class ResNet(FederatedModule):
         self.avgpool = bnn.GlobalAvgPool()
         self.fc = bnn.Linear(512 * block.expansion, num_classes, out_fp32=True)
         self.stats_workspace = None
+        self.zeroes_own_workspace = True   # forward() clears the statistics workspace itself
         for m in self.modules():   # zero-init the last BN of each block (standard recipe; keeps early training stable)
             if isinstance(m, BasicBlock):
                 nn.init.zeros_(m.bn2.weight)
@@ -116,6 +117,8 @@ class ResNet(FederatedModule):
 
     def forward(self, x):
         """``x``: NHWC ``[N, H, W, C]`` (bf16 on CUDA)."""
+        if self.stats_workspace is not None and self.training:
+            self.stats_workspace.zero_()      # ONE memset per step: forward and backward statistic sums of every BN
         x = self.maxpool(self.bn1(self.conv1(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(self.avgpool(x))

@@ -113,7 +113,7 @@ class GraphedLocalSGD:
         xb = F.gather_rows(X, idx)
         yb = F.gather_rows(y, idx) if y.dtype == torch.int64 and y.dim() == 1 else y.index_select(0, idx)
         ws = getattr(self.model, "stats_workspace", None)
-        if ws is not None:
+        if ws is not None and not getattr(self.model, "zeroes_own_workspace", False):
             ws.zero_()
         out = self.model(xb)
         loss, stats = self._loss(out, yb)
