@@ -63,6 +63,20 @@ void gemm_batched(const at::Tensor& a, const at::Tensor& b, at::Tensor d, int64_
         "gemm_bf16_batched");
 }
 
+// experimental fused attention forward (S = 128, d_head = 64); returns false when the shape is unsupported
+bool attention_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor probs, int64_t B, int64_t S, int64_t H, int64_t dh,
+                   double scale) {
+  CHECK_CUDA(qkv); CHECK_CUDA(out); CHECK_CUDA(probs);
+  TORCH_CHECK(qkv.scalar_type() == at::kBFloat16 && out.scalar_type() == at::kBFloat16 &&
+              probs.scalar_type() == at::kBFloat16 && qkv.is_contiguous() && out.is_contiguous() && probs.is_contiguous());
+  const c10::cuda::CUDAGuard guard(qkv.device());
+  const int rc = b200_attention_fwd(cptr(qkv), ptr(out), ptr(probs), static_cast<int>(B), static_cast<int>(S),
+                                    static_cast<int>(H), static_cast<int>(dh), static_cast<float>(scale), cur_stream());
+  if (rc == -2) return false;
+  check(rc, "attention_fwd");
+  return true;
+}
+
 void gemm_fp8(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::optional<at::Tensor>& bias,
               const std::optional<at::Tensor>& sfa, const std::optional<at::Tensor>& sfb, int64_t M, int64_t N, int64_t K,
               int64_t lda, int64_t ldb, int64_t ldd, int64_t act, int64_t split_k, bool accumulate, double alpha) {
@@ -398,6 +412,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "baton_b200 sm_100a kernels";
   m.attr("MAX_RANKS") = B200_MAX_RANKS;
   m.def("gemm", &gemm);
+  m.def("attention_fwd", &attention_fwd);
   m.def("gemm_batched", &gemm_batched);
   m.def("gemm_fp8", &gemm_fp8);
   m.def("quant_mx_rows", &quant_mx_rows);

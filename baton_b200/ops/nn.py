@@ -603,6 +603,9 @@ def mse_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
 
 
 # ================================================================================ attention / embedding (BERT)
+_FUSED_ATTN = __import__("os").environ.get("BATON_FUSED_ATTN", "0") == "1"   # opt-in until validated on hardware
+
+
 class _AttnFn(torch.autograd.Function):
     """Multi-head self-attention core on a packed ``qkv [B*S, 3*H*dh]`` buffer: four strided-batched
     tcgen05 GEMMs + the row-softmax kernel forward, five GEMMs + softmax backward; Q/K/V and their
@@ -611,6 +614,14 @@ class _AttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, B, S, H, dh):
         D = H * dh
+        if _FUSED_ATTN and S == 128 and dh == 64:
+            # experimental single-kernel forward (csrc/attention.cu): scores stay in TMEM, P is written once
+            probs = torch.empty((B * H * S, S), dtype=BF16, device=qkv.device)
+            out = torch.empty((B * S, D), dtype=BF16, device=qkv.device)
+            if load().attention_fwd(qkv, out, probs, B, S, H, dh, 1.0 / math.sqrt(dh)):
+                ctx.save_for_backward(qkv, probs)
+                ctx.dims = (B, S, H, dh)
+                return out
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         scores = torch.empty((B * H * S, S), dtype=BF16, device=qkv.device)
         F.gemm_batched(q, k, scores, M=S, N=S, K=dh, lda=3 * D, ldb=3 * D, ldd=S, a_mn=False, b_mn=False,

@@ -1,6 +1,7 @@
 """BERT tier: strided-batched tcgen05 GEMM, fused attention core, embedding, and the BERT encoder
 against fp32 PyTorch references."""
 import math
+import os
 
 import pytest
 import torch
@@ -81,3 +82,25 @@ def test_bert_tiny_matches_fp32_reference_and_trains():
     m._graphed_trainer = tr
     hist = m.train(X, yy, n_epoch=8, lr=0.05, batch_size=32)
     assert hist[-1] < hist[0], hist
+
+
+@pytest.mark.skipif(os.environ.get("BATON_FUSED_ATTN") != "1",
+                    reason="experimental single-kernel attention forward: opt in with BATON_FUSED_ATTN=1")
+def test_fused_attention_forward_matches_three_kernel_path():
+    from baton_b200.ops import nn as bnn
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    B, S, H, dh = 8, 128, 12, 64
+    D = H * dh
+    qkv = (torch.randn(B * S, 3 * D, device=dev) * 0.5).to(BF16)
+    outs = []
+    for fused in (False, True):
+        bnn._FUSED_ATTN = fused
+        x = qkv.clone().requires_grad_(True)
+        out = bnn.attention(x, B, S, H, dh)
+        g = torch.ones_like(out)
+        out.backward(g)
+        outs.append((out.detach().float(), x.grad.float()))
+    bnn._FUSED_ATTN = True
+    assert _rel(outs[1][0], outs[0][0]) < 2e-2
+    assert _rel(outs[1][1], outs[0][1]) < 3e-2
