@@ -350,6 +350,22 @@ void bn_bwd_apply(const at::Tensor& x, const at::Tensor& y, const at::Tensor& dy
                           cur_stream()),
         "bn_bwd_apply");
 }
+// experimental single-kernel BatchNorm backward; false = shape not supported, use reduce + apply
+bool bn_bwd_fused(const at::Tensor& x, const at::Tensor& y, const at::Tensor& dy, at::Tensor dx,
+                  const std::optional<at::Tensor>& dres, const std::optional<at::Tensor>& gamma, const at::Tensor& mean,
+                  const at::Tensor& rstd, at::Tensor sums, const std::optional<at::Tensor>& dgamma,
+                  const std::optional<at::Tensor>& dbeta, int64_t rows, int64_t C, bool relu, at::Tensor barrier) {
+  CHECK_CUDA(x);
+  TORCH_CHECK(barrier.scalar_type() == at::kInt && barrier.numel() >= 2, "barrier: int32[2], zero-initialised");
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rc = b200_bn_bwd_fused(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(), opt_ptr<void>(dres),
+                                   opt_ptr<const float>(gamma), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                                   sums.data_ptr<float>(), opt_ptr<float>(dgamma), opt_ptr<float>(dbeta), rows, C, relu,
+                                   reinterpret_cast<unsigned int*>(barrier.data_ptr<int>()), cur_stream());
+  if (rc == -2) return false;
+  check(rc, "bn_bwd_fused");
+  return true;
+}
 void layernorm_fwd(const at::Tensor& x, const std::optional<at::Tensor>& res, at::Tensor y, const at::Tensor& gamma,
                    const at::Tensor& beta, at::Tensor mean, at::Tensor rstd, int64_t rows, int64_t C, double eps) {
   CHECK_CUDA(x);
@@ -413,6 +429,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("MAX_RANKS") = B200_MAX_RANKS;
   m.def("gemm", &gemm);
   m.def("attention_fwd", &attention_fwd);
+  m.def("bn_bwd_fused", &bn_bwd_fused);
   m.def("gemm_batched", &gemm_batched);
   m.def("gemm_fp8", &gemm_fp8);
   m.def("quant_mx_rows", &quant_mx_rows);

@@ -113,6 +113,9 @@ int b200_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float
 int b200_bn_bwd_apply(const void* x, const void* y, const void* dy, void* dx, void* dres, const float* gamma,
                       const float* save_mean, const float* save_rstd, float* sums, float* dgamma, float* dbeta,
                       long long rows, int C, int relu, cudaStream_t stream);
+int b200_bn_bwd_fused(const void* x, const void* y, const void* dy, void* dx, void* dres, const float* gamma,
+                      const float* save_mean, const float* save_rstd, float* sums, float* dgamma, float* dbeta,
+                      long long rows, int C, int relu, unsigned int* barrier, cudaStream_t stream);
 int b200_layernorm_fwd(const void* x, const void* residual, void* y, const float* gamma, const float* beta,
                        float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t stream);
 int b200_layernorm_bwd(const void* x, const void* dy, void* dx, const float* gamma, const float* mean,

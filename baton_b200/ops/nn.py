@@ -352,6 +352,18 @@ class Conv2d(nn.Module):
 
 
 # ================================================================================ BatchNorm (+residual +ReLU)
+_BN_BWD_FUSED = __import__("os").environ.get("BATON_BN_BWD_FUSED", "0") == "1"   # opt-in until validated on hardware
+_GRID_BARRIERS = {}
+
+
+def _grid_barrier_words(device):
+    """{count, generation} words of the device-wide barrier used by the single-kernel BatchNorm backward."""
+    buf = _GRID_BARRIERS.get(device)
+    if buf is None:
+        buf = _GRID_BARRIERS[device] = torch.zeros(2, dtype=torch.int32, device=device)
+    return buf
+
+
 class _BNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, gamma, beta, rmean, rvar, nbt, eps, momentum, relu, training, ws, anchor,
@@ -384,14 +396,19 @@ class _BNFn(torch.autograd.Function):
         gamma, beta = ctx.gamma, ctx.beta
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if ctx.has_res else None
-        C_.bn_bwd_reduce(x, y, dy, mean, rstd, ctx.sums_b, ctx.rows, ctx.c, ctx.relu)
         tg, tb = _grad_target(gamma), _grad_target(beta)
         gg = gb = None
         if tg is None:
             gg = tg = torch.zeros(ctx.c, dtype=torch.float32, device=x.device)
         if tb is None:
             gb = tb = torch.zeros(ctx.c, dtype=torch.float32, device=x.device)
-        C_.bn_bwd_apply(x, y, dy, dx, dres, gamma, mean, rstd, ctx.sums_b, tg, tb, ctx.rows, ctx.c, ctx.relu)
+        done = False
+        if _BN_BWD_FUSED:       # experimental: reduce + device-wide barrier + apply in one kernel
+            done = C_.bn_bwd_fused(x, y, dy, dx, dres, gamma, mean, rstd, ctx.sums_b, tg, tb, ctx.rows, ctx.c, ctx.relu,
+                                   _grid_barrier_words(x.device))
+        if not done:
+            C_.bn_bwd_reduce(x, y, dy, mean, rstd, ctx.sums_b, ctx.rows, ctx.c, ctx.relu)
+            C_.bn_bwd_apply(x, y, dy, dx, dres, gamma, mean, rstd, ctx.sums_b, tg, tb, ctx.rows, ctx.c, ctx.relu)
         if ctx.has_res and dres is None:
             dres = dy
         return dx, dres, gg, gb, None, None, None, None, None, None, None, None, None, None
