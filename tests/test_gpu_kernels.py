@@ -1,7 +1,6 @@
 """Kernel-correctness tier: every sm_100a kernel against a plain PyTorch fp32
 reference of the same op."""
 import math
-
 import os
 
 import pytest
