@@ -214,7 +214,7 @@ void fedavg_allreduce(const std::vector<int64_t>& wire_ptrs, const std::vector<i
                       bool counts_from_flags, int64_t alive_mask, int64_t rank, int64_t world, int64_t wire_kind,
                       bool delta, bool use_nvls, int64_t epoch, const std::optional<at::Tensor>& tile_flags,
                       int64_t flag_value, int64_t tile_elems, int64_t n_ctas, int64_t timeout_log2,
-                      const std::optional<at::Tensor>& status) {
+                      const std::optional<at::Tensor>& status, const std::optional<at::Tensor>& phase_ns) {
   CHECK_CUDA(theta);
   TORCH_CHECK(world <= B200_MAX_RANKS && static_cast<int64_t>(wire_ptrs.size()) == world &&
               static_cast<int64_t>(pad_ptrs.size()) == world && static_cast<int64_t>(n_samples.size()) == world);
@@ -254,6 +254,11 @@ void fedavg_allreduce(const std::vector<int64_t>& wire_ptrs, const std::vector<i
   a.tile_elems = static_cast<int>(tile_elems);
   a.timeout_log2 = static_cast<int>(timeout_log2);
   a.status = opt_ptr<int>(status);
+  a.phase_ns = nullptr;
+  if (phase_ns.has_value()) {
+    TORCH_CHECK(phase_ns->scalar_type() == at::kLong && phase_ns->numel() >= 16, "phase_ns: int64[16]");
+    a.phase_ns = reinterpret_cast<unsigned long long*>(phase_ns->data_ptr<int64_t>());
+  }
   TORCH_CHECK(!delta || a.global_w != nullptr, "delta mode needs the global copy");
   TORCH_CHECK(!use_nvls || a.wire_mc != nullptr, "NVLS mode needs the multicast address");
   check(b200_fedavg_allreduce(&a, static_cast<int>(n_ctas), cur_stream()), "fedavg_allreduce");

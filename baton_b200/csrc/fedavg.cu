@@ -170,6 +170,16 @@ __device__ __forceinline__ int quad_block_exponent(const float (&f)[VEC]) {
   return mx_exponent(amax);
 }
 
+// Optional in-kernel phase timestamps (multi-GPU kernels with spin barriers cannot be replayed under ncu):
+// thread 0 of the first and of the last CTA record %globaltimer at every phase boundary.
+__device__ __forceinline__ void phase_stamp(const FedAvgArgs& a, int slot) {
+  if (a.phase_ns != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.phase_ns[(blockIdx.x == 0 ? 0 : 8) + slot] = t;
+  }
+}
+
 template <int WIRE>
 __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(const __grid_constant__ FedAvgArgs a) {
   using W = Wire<WIRE>;
@@ -212,6 +222,7 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
   // the scaled value on the wire because the switch can only add: scale by n_k now, by 1/N in phase 2.
   // Loop bounds are warp-uniform (first lane's element) so the block-scale shuffles are legal.
   const float pack_scale = a.use_nvls ? my_n * a.nvls_prescale : 1.0f;
+  phase_stamp(a, 0);                                   // start
   if (my_n != 0.f || a.use_nvls) {
     for (long long q = blockIdx.x; q * A < n_tiles; q += G) {
       for (int r = 0; r < A; ++r) {
@@ -272,7 +283,9 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
     for (int i = threadIdx.x; i < a.n_int; i += FEDAVG_THREADS) a.int_wire[a.rank][i] = a.int_local[i];
     for (int i = threadIdx.x; i < a.n_loss; i += FEDAVG_THREADS) a.loss_wire[a.rank][i] = a.loss_local[i];
   }
+  phase_stamp(a, 1);                                   // pack done
   if (!cta_barrier_all_ranks(a, a.epoch + 1, __float_as_uint(my_n), s_payload)) return;
+  phase_stamp(a, 2);                                   // barrier 1 passed
 
   // weights w_k = n_k / N from the counts that rode on the barrier flags (or the host's plan)
   if (threadIdx.x == 0) {
@@ -363,7 +376,9 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
       a.loss_out[e] = acc;
     }
   }
+  phase_stamp(a, 3);                                   // reduce + broadcast done
   if (!cta_barrier_all_ranks(a, a.epoch + 2, 0u, nullptr)) return;
+  phase_stamp(a, 4);                                   // barrier 2 passed
 
   // ---------------------------------------------------------------- phase 2: running-mean apply
   // CTA b applies exactly the tiles CTA b of the owners produced: (t / A) % G == b
@@ -442,7 +457,9 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
   }
   // closing barrier: nobody may start the next round's phase 0 (overwriting its wire buffer, which
   // peers pushed results into) or reuse int/loss wire pages while a peer still reads them
+  phase_stamp(a, 5);                                   // apply done
   cta_barrier_all_ranks(a, a.epoch + 3, 0u, nullptr);
+  phase_stamp(a, 6);                                   // closing barrier passed
 }
 
 // stand-alone cross-GPU barrier on the pads (one CTA): fences host-side phases

@@ -86,6 +86,7 @@ struct FedAvgArgs {
   int tile_elems;                   // arena tile size in elements
   int timeout_log2;                 // spin limit (2^k polls) before the kernel gives up, 0 = none
   int* status;                      // device int: set non-zero on barrier timeout
+  unsigned long long* phase_ns;     // optional [16]: %globaltimer at the phase boundaries (first / last CTA), or nullptr
 };
 int b200_fedavg_allreduce(const FedAvgArgs* args, int n_ctas, cudaStream_t stream);
 int b200_flag_barrier(unsigned long long* const* pads, int rank, int world, uint32_t alive_mask, uint32_t epoch,

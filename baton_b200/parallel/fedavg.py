@@ -73,9 +73,27 @@ class FedAvgSession:
         # GEMM that is launched right behind it on the compute stream
         self.stream = torch.cuda.Stream(device=self.device, priority=-1) if self.device.type == "cuda" else None
         self.symm.barrier()
+        self.phase_ns = None       # enable_phase_timing(): int64[16] of %globaltimer stamps written by the kernel
         self.nvls_choice = "forced" if nvls != "auto" else "default"
         if nvls == "auto" and self.use_nvls and self.delta and self.world > 1 and arena.global_w is not None:
             self.autotune_nvls()
+
+    PHASES = ("pack", "barrier1", "reduce_bcast", "barrier2", "apply", "barrier3")
+
+    def enable_phase_timing(self) -> None:
+        """Ask the kernel to record %globaltimer at its phase boundaries (first and last CTA) -- the way to
+        see where a multi-GPU round goes, since kernels with cross-GPU spin barriers cannot run under ncu."""
+        self.phase_ns = torch.zeros(16, dtype=torch.int64, device=self.device)
+
+    def phase_breakdown_us(self) -> dict:
+        """Phase durations of the LAST launch in microseconds: ``{"first_cta": {...}, "last_cta": {...}}``."""
+        if self.phase_ns is None:
+            return {}
+        t = self.phase_ns.tolist()
+        out = {}
+        for name, base in (("first_cta", 0), ("last_cta", 8)):
+            out[name] = {p: (t[base + i + 1] - t[base + i]) / 1e3 for i, p in enumerate(self.PHASES)}
+        return out
 
     def autotune_nvls(self, iters: int = 3) -> None:
         """Measure, don't guess: time the collective both ways (peer loads/stores vs in-switch
@@ -155,7 +173,7 @@ class FedAvgSession:
                 self.loss_local, self.symm.peer_ptrs(self.off_loss), self.loss_out,
                 counts, from_flags, mask, self.rank, world, self.wire_kind, self.delta,
                 bool(self.use_nvls and len(alive) == world), self.epoch,
-                self.tile_flags, flag_value, tile, self.n_ctas, self.timeout_log2, self.status)
+                self.tile_flags, flag_value, tile, self.n_ctas, self.timeout_log2, self.status, self.phase_ns)
         self.epoch = (self.epoch + 3) & 0xFFFFFFFF     # uint32 wrap: the kernel compares signed differences
         self.rounds += 1
         self._side_pending = on_side_stream

@@ -63,6 +63,13 @@ def main():
                     torch.cuda.synchronize()
                     if it >= 3:
                         times.append(e0.elapsed_time(e1) * 1e3)
+                if os.environ.get("AGG_PHASES") == "1" and hasattr(sess, "enable_phase_timing"):
+                    sess.enable_phase_timing()
+                    sess.aggregate(my_n=float(100 + rank))
+                    torch.cuda.synchronize()
+                    if rank == 0:
+                        print("   phases(us)", {k: {p: round(v, 1) for p, v in d.items()}
+                                                for k, d in sess.phase_breakdown_us().items()}, flush=True)
                 t = torch.tensor([min(times), sum(times) / len(times)], device=dev, dtype=torch.float64)
                 if world > 1:
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)
