@@ -23,7 +23,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "csrc", "build")
 TARGET = os.path.join(HERE, "_C.so")
 
-CU_SOURCES = ["gemm_tcgen05.cu", "gemm_fp8.cu", "quant.cu", "attention.cu", "gemm_simt.cu", "fedavg.cu", "elementwise.cu", "conv.cu", "norm.cu", "loss.cu"]
+CU_SOURCES = ["gemm_tcgen05.cu", "gemm_fp8.cu", "quant.cu", "attention.cu", "im2col_tma.cu", "gemm_simt.cu", "fedavg.cu", "elementwise.cu", "conv.cu", "norm.cu", "loss.cu"]
 HEADERS = ["ptx.cuh", "launch.h", "pdl.cuh", "mx.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]

@@ -77,6 +77,22 @@ bool attention_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor probs, int6
   return true;
 }
 
+// experimental: explicit-im2col-layout dump of TMA im2col loads (semantics probe for the implicit-GEMM conv)
+bool im2col_tma_probe(const at::Tensor& x, at::Tensor col, int64_t kh, int64_t kw, int64_t stride, int64_t pad,
+                      int64_t ho, int64_t wo) {
+  CHECK_CUDA(x); CHECK_CUDA(col);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && col.scalar_type() == at::kBFloat16 && x.dim() == 4 && x.is_contiguous() &&
+              col.is_contiguous());
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rc = b200_im2col_tma_probe(cptr(x), ptr(col), static_cast<int>(x.size(0)), static_cast<int>(x.size(1)),
+                                       static_cast<int>(x.size(2)), static_cast<int>(x.size(3)), static_cast<int>(kh),
+                                       static_cast<int>(kw), static_cast<int>(stride), static_cast<int>(pad),
+                                       static_cast<int>(ho), static_cast<int>(wo), cur_stream());
+  if (rc == -2) return false;
+  check(rc, "im2col_tma_probe");
+  return true;
+}
+
 void gemm_fp8(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::optional<at::Tensor>& bias,
               const std::optional<at::Tensor>& sfa, const std::optional<at::Tensor>& sfb, int64_t M, int64_t N, int64_t K,
               int64_t lda, int64_t ldb, int64_t ldd, int64_t act, int64_t split_k, bool accumulate, double alpha) {
@@ -435,6 +451,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm", &gemm);
   m.def("attention_fwd", &attention_fwd);
   m.def("bn_bwd_fused", &bn_bwd_fused);
+  m.def("im2col_tma_probe", &im2col_tma_probe);
   m.def("gemm_batched", &gemm_batched);
   m.def("gemm_fp8", &gemm_fp8);
   m.def("quant_mx_rows", &quant_mx_rows);

@@ -21,6 +21,9 @@ int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int M, int N, 
 // ---- attention.cu (experimental fused attention forward, S = 128, d_head = 64)
 int b200_attention_fwd(const void* qkv, void* out, void* probs, int B, int S, int H, int dh, float scale,
                        cudaStream_t stream);
+// ---- im2col_tma.cu (experimental: TMA im2col tensor maps, probe kernel only)
+int b200_im2col_tma_probe(const void* x, void* col, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
+                          int Ho, int Wo, cudaStream_t stream);
 // ---- gemm_fp8.cu / quant.cu (MXFP8: e4m3 + UE8M0 scale per 32 elements of K)
 int b200_gemm_fp8(const void* a, const void* b, void* d, const float* bias, const void* sfa, const void* sfb, int M, int N,
                   int K, long long lda, long long ldb, long long ldd, int out_fp32, int act, int split_k, int accumulate,

@@ -195,6 +195,22 @@ def test_conv_bn_fused_statistics_match_separate_pass(bnn):
     assert _rel(g1, g0) < 2e-2
 
 
+@pytest.mark.skipif(os.environ.get("BATON_TMA_IM2COL") != "1",
+                    reason="experimental TMA im2col probe (implicit-GEMM ground work): opt in with BATON_TMA_IM2COL=1")
+@pytest.mark.parametrize("c,k,stride,pad,h", [(64, 3, 1, 1, 8), (128, 3, 2, 1, 8), (64, 1, 2, 0, 8), (256, 3, 1, 1, 2)])
+def test_tma_im2col_probe_matches_explicit_im2col(F, c, k, stride, pad, h):
+    from baton_b200.ops import load
+    torch.manual_seed(c + k)
+    dev = _dev()
+    x = torch.randn(32, h, h, c, device=dev).to(BF16)
+    ref, ho, wo, kp = F.im2col(x, k, k, stride, pad)
+    assert kp == k * k * c
+    col = torch.zeros_like(ref)
+    assert load().im2col_tma_probe(x, col, k, k, stride, pad, ho, wo)
+    torch.cuda.synchronize()
+    assert torch.equal(col, ref)
+
+
 def test_gemm_simt_fallback_small_pitch(F):
     torch.manual_seed(2)
     dev = _dev()
