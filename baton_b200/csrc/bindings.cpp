@@ -93,6 +93,41 @@ bool im2col_tma_probe(const at::Tensor& x, at::Tensor col, int64_t kh, int64_t k
   return true;
 }
 
+// experimental implicit-GEMM convolution; false = shape not supported (caller falls back to im2col + GEMM)
+bool conv_igemm_fwd(const at::Tensor& x, const at::Tensor& w, at::Tensor y, int64_t kh, int64_t kw, int64_t stride,
+                    int64_t pad, int64_t ho, int64_t wo, int64_t cluster_k, int64_t force_bn,
+                    const std::optional<at::Tensor>& col_stats) {
+  CHECK_CUDA(x); CHECK_CUDA(w); CHECK_CUDA(y);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && y.scalar_type() == at::kBFloat16 &&
+              x.dim() == 4 && x.is_contiguous() && w.is_contiguous() && y.is_contiguous());
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rc = b200_conv_igemm_fwd(cptr(x), cptr(w), ptr(y), static_cast<int>(x.size(0)), static_cast<int>(x.size(1)),
+                                     static_cast<int>(x.size(2)), static_cast<int>(x.size(3)), static_cast<int>(w.size(0)),
+                                     static_cast<int>(kh), static_cast<int>(kw), static_cast<int>(stride),
+                                     static_cast<int>(pad), static_cast<int>(ho), static_cast<int>(wo),
+                                     static_cast<int>(cluster_k), static_cast<int>(force_bn), opt_ptr<float>(col_stats),
+                                     cur_stream());
+  if (rc == -2) return false;
+  check(rc, "conv_igemm_fwd");
+  return true;
+}
+bool conv_igemm_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_t cout, int64_t kh, int64_t kw,
+                      int64_t stride, int64_t pad, int64_t ho, int64_t wo, int64_t split_k, int64_t force_bn) {
+  CHECK_CUDA(dy); CHECK_CUDA(x); CHECK_CUDA(dw);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && dy.scalar_type() == at::kBFloat16 && dw.scalar_type() == at::kFloat &&
+              x.dim() == 4 && x.is_contiguous() && dy.is_contiguous());
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rc = b200_conv_igemm_wgrad(cptr(dy), cptr(x), dw.data_ptr<float>(), static_cast<int>(x.size(0)),
+                                       static_cast<int>(x.size(1)), static_cast<int>(x.size(2)), static_cast<int>(x.size(3)),
+                                       static_cast<int>(cout), static_cast<int>(kh), static_cast<int>(kw),
+                                       static_cast<int>(stride), static_cast<int>(pad), static_cast<int>(ho),
+                                       static_cast<int>(wo), static_cast<int>(split_k), static_cast<int>(force_bn),
+                                       cur_stream());
+  if (rc == -2) return false;
+  check(rc, "conv_igemm_wgrad");
+  return true;
+}
+
 void gemm_fp8(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::optional<at::Tensor>& bias,
               const std::optional<at::Tensor>& sfa, const std::optional<at::Tensor>& sfb, int64_t M, int64_t N, int64_t K,
               int64_t lda, int64_t ldb, int64_t ldd, int64_t act, int64_t split_k, bool accumulate, double alpha) {
@@ -452,6 +487,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attention_fwd", &attention_fwd);
   m.def("bn_bwd_fused", &bn_bwd_fused);
   m.def("im2col_tma_probe", &im2col_tma_probe);
+  m.def("conv_igemm_fwd", &conv_igemm_fwd);
+  m.def("conv_igemm_wgrad", &conv_igemm_wgrad);
   m.def("gemm_batched", &gemm_batched);
   m.def("gemm_fp8", &gemm_fp8);
   m.def("quant_mx_rows", &quant_mx_rows);

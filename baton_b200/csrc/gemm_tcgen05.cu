@@ -64,6 +64,11 @@ struct GemmParams {
   int batched, batch_inner;
   int batch_count;         // persistent batched mode: number of z slices
   long long d_outer, d_inner;
+  // implicit-GEMM convolution (CONV template modes; appended last so existing field offsets do not move)
+  int conv_ho, conv_wo;    // output image size
+  int conv_stride, conv_pad;
+  int conv_kw;             // filter width (tap = r * kw + s)
+  int conv_cin;            // input channels (multiple of 64)
 };
 
 template <int BN>
@@ -228,7 +233,10 @@ __device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, in
 }
 
 // ---- fixed-depth pipeline, one CTA per SM: the default path ----
-template <int BN, int STAGES>
+// CONV: 0 = plain GEMM; 1 = implicit-GEMM conv forward (A = im2col(x) gathered by TMA im2col, k-tile = one filter
+// tap x 64 input channels); 2 = implicit wgrad (B = im2col(x) MN-major, k-tile = 64 output pixels, every 64-wide
+// N atom = one tap x 64 channels).  EXPERIMENTAL modes, see csrc/im2col_tma.cu.
+template <int BN, int STAGES, int CONV = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
@@ -304,7 +312,12 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint8_t* sa = smem + s * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
         const int k0 = (kt_begin + i) * BK;
-        mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        if constexpr (CONV == 2) {
+          const int live = (p.N - n0 + 63) / 64 < BN / 64 ? (p.N - n0 + 63) / 64 : BN / 64;
+          mbar_expect_tx(&full_bar[s], L::A_BYTES + live * 8192);
+        } else {
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+        }
         if (p.batched) {
           if (!p.a_mn) {
             tma_load_4d(sa, &tmA, &full_bar[s], k0, m0, bz_inner, bz_outer);
@@ -321,14 +334,37 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               tma_load_4d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0, bz_inner, bz_outer);
           }
         } else {
-        if (!p.a_mn) {
+        if constexpr (CONV == 1) {
+          // k-tile -> (filter tap, 64-channel block); base pixel of this CTA's 128 output pixels in input coords
+          const int kt = kt_begin + i;
+          const int cblocks = p.conv_cin >> 6;
+          const int tap = kt / cblocks, cb = kt - tap * cblocks;
+          const int fr = tap / p.conv_kw, fs = tap - fr * p.conv_kw;
+          const int q0 = m0 % p.conv_wo, t0 = m0 / p.conv_wo;
+          tma_load_im2col_4d(sa, &tmA, &full_bar[s], cb * 64, q0 * p.conv_stride - p.conv_pad,
+                             (t0 % p.conv_ho) * p.conv_stride - p.conv_pad, t0 / p.conv_ho, fs, fr);
+        } else if (!p.a_mn) {
           tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box [64 k][128 rows]
         } else {
 #pragma unroll
           for (int j = 0; j < BM / 64; ++j)  // box [64 m][64 k rows] per MN atom
             tma_load_2d(sa + j * 8192, &tmA, &full_bar[s], m0 + j * 64, k0);
         }
-        if (!p.b_mn) {
+        if constexpr (CONV == 2) {
+          // k-tile = 64 output pixels starting at k0; N atom j = (tap, channel block) of column n0 + 64 j
+          const int q0 = k0 % p.conv_wo, t0 = k0 / p.conv_wo;
+          const int w0 = q0 * p.conv_stride - p.conv_pad, h0 = (t0 % p.conv_ho) * p.conv_stride - p.conv_pad;
+          const int img = t0 / p.conv_ho;
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) {
+            const int col = n0 + j * 64;
+            if (col < p.N) {          // atoms past the last tap are never stored: leave them (expect_tx below)
+              const int tap = col / p.conv_cin, c = col - tap * p.conv_cin;
+              const int fr = tap / p.conv_kw, fs = tap - fr * p.conv_kw;
+              tma_load_im2col_4d(sb + j * 8192, &tmB, &full_bar[s], c, w0, h0, img, fs, fr);
+            }
+          }
+        } else if (!p.b_mn) {
           tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box [64 k][BN rows]
         } else {
 #pragma unroll
@@ -849,7 +885,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // ---- runtime-depth pipeline + cluster split-K (DSMEM reduce) ----
-template <int BN, bool CLUSTER>
+template <int BN, bool CLUSTER, int CONV = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
@@ -928,7 +964,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint8_t* sb = sa + L::A_BYTES;
         const int k0 = (kt_begin + i) * BK;
         mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        if (!p.a_mn) {
+        if constexpr (CONV == 1) {
+          const int kt = kt_begin + i;
+          const int cblocks = p.conv_cin >> 6;
+          const int tap = kt / cblocks, cb = kt - tap * cblocks;
+          const int fr = tap / p.conv_kw, fs = tap - fr * p.conv_kw;
+          const int q0 = m0 % p.conv_wo, t0 = m0 / p.conv_wo;
+          tma_load_im2col_4d(sa, &tmA, &full_bar[s], cb * 64, q0 * p.conv_stride - p.conv_pad,
+                             (t0 % p.conv_ho) * p.conv_stride - p.conv_pad, t0 / p.conv_ho, fs, fr);
+        } else if (!p.a_mn) {
           tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);  // box [64 k][128 rows]
         } else {
 #pragma unroll
@@ -1128,18 +1172,18 @@ static int make_map4(CUtensorMap* map, const void* base, long long rows, long lo
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CONV = 0>
 static int launch_fixed(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
                       cudaStream_t stream) {
   constexpr int smem = STAGES * SmemLayout<BN>::STAGE_BYTES + (2 * STAGES + 1) * 8 + 16 + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_fixed_kernel<BN, STAGES>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_fixed_kernel<BN, STAGES, CONV>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
-  cudaError_t le = launch_pdl(gemm_bf16_fixed_kernel<BN, STAGES>, grid, GEMM_THREADS, smem, stream, ta, tb, p);
+  cudaError_t le = launch_pdl(gemm_bf16_fixed_kernel<BN, STAGES, CONV>, grid, GEMM_THREADS, smem, stream, ta, tb, p);
   if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
@@ -1188,7 +1232,7 @@ static int launch_persistent(const CUtensorMap& ta, const CUtensorMap& tb, const
   return static_cast<int>(cudaGetLastError());
 }
 
-template <int BN>
+template <int BN, int CONV = 0>
 static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
                       cudaStream_t stream) {
   using L = SmemLayout<BN>;
@@ -1197,10 +1241,10 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   static bool configured = false;
   if (!configured) {
     const int cap = max_smem > L::PART_BYTES + 4096 ? max_smem : L::PART_BYTES + 4096;
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, false>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, false, CONV>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+      e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN, true, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
@@ -1239,8 +1283,8 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t le = p.cluster_k > 1 ? cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true>, ta, tb, p)
-                                   : cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, false>, ta, tb, p);
+  cudaError_t le = p.cluster_k > 1 ? cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, true, CONV>, ta, tb, p)
+                                   : cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<BN, false, CONV>, ta, tb, p);
   if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
@@ -1416,4 +1460,87 @@ extern "C" int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int
   if (bn == 256) return launch_fixed<256, 4>(ta, tb, p, grid, stream);
   if (bn == 128) return launch_fixed<128, 6>(ta, tb, p, grid, stream);
   return launch_fixed<64, 8>(ta, tb, p, grid, stream);
+}
+
+// ---- implicit-GEMM convolution (EXPERIMENTAL, opt-in from Python with BATON_CONV_IGEMM=1) ---------------------
+extern "C" int b200_encode_map_im2col_bf16(void* map, const void* x, int N, int H, int W, int C, int KH, int KW,
+                                            int stride, int pad, int channels, int pixels);
+
+// forward: y[N*Ho*Wo, Cout] = im2col(x) w^T with x NHWC bf16 (Cin % 64 == 0), w [Cout, KH*KW*Cin] (channels_last)
+extern "C" int b200_conv_igemm_fwd(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int KH,
+                                   int KW, int stride, int pad, int Ho, int Wo, int cluster_k, int force_bn,
+                                   float* col_stats, cudaStream_t stream) {
+  using namespace b200;
+  const long long M = static_cast<long long>(N) * Ho * Wo;
+  const int K = KH * KW * Cin;
+  if (M <= 0 || Cout <= 0) return 0;
+  if (Cin % 64 != 0 || Cout % 8 != 0 || M > (1ll << 30) || (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(y) & 15))
+    return -2;
+  const int bn = force_bn > 0 ? force_bn : (Cout > 128 ? 256 : (Cout > 64 ? 128 : 64));
+  CUtensorMap ta, tb;
+  int rc = b200_encode_map_im2col_bf16(&ta, x, N, H, W, Cin, KH, KW, stride, pad, 64, BM);
+  if (rc) return rc;
+  rc = make_map(&tb, w, Cout, K, K, BK, bn);
+  if (rc) return rc;
+  const int k_tiles = K / BK;
+  if (cluster_k != 1 && cluster_k != 2 && cluster_k != 4 && cluster_k != 8) return -5;
+  while (cluster_k > 1 && (cluster_k - 1) * ((k_tiles + cluster_k - 1) / cluster_k) >= k_tiles) cluster_k >>= 1;
+  const int per = (k_tiles + cluster_k - 1) / cluster_k;
+  GemmParams p;
+  p.M = static_cast<int>(M); p.N = Cout; p.K = K; p.D = y; p.ldd = Cout; p.bias = nullptr; p.out_fp32 = 0; p.act = 0;
+  p.a_mn = 0; p.b_mn = 0; p.k_tiles_per_split = per; p.cluster_k = cluster_k; p.atomic_out = 0;
+  p.epi_staged = 0; p.col_stats = col_stats;
+  p.tile_flags = nullptr; p.flag_epoch = 0; p.alpha = 1.0f; p.flag_elem_off = 0; p.flag_tile_elems = 0; p.ldb = K;
+  p.flag_bias_off = -1;
+  p.batched = 0; p.batch_inner = 1; p.batch_count = 1; p.d_outer = 0; p.d_inner = 0;
+  const int max_stages = (bn == 256) ? 4 : (bn == 128 ? 6 : 8);
+  p.stages = per < max_stages ? (per < 2 ? 2 : per) : max_stages;
+  p.conv_ho = Ho; p.conv_wo = Wo; p.conv_stride = stride; p.conv_pad = pad; p.conv_kw = KW; p.conv_cin = Cin;
+  dim3 grid((Cout + bn - 1) / bn, static_cast<unsigned>((M + BM - 1) / BM), cluster_k);
+  if (cluster_k > 1) {
+    if (bn == 256) return launch_cfg<256, 1>(ta, tb, p, grid, stream);
+    if (bn == 128) return launch_cfg<128, 1>(ta, tb, p, grid, stream);
+    return launch_cfg<64, 1>(ta, tb, p, grid, stream);
+  }
+  if (bn == 256) return launch_fixed<256, 4, 1>(ta, tb, p, grid, stream);
+  if (bn == 128) return launch_fixed<128, 6, 1>(ta, tb, p, grid, stream);
+  return launch_fixed<64, 8, 1>(ta, tb, p, grid, stream);
+}
+
+// weight gradient: dw[Cout, KH*KW*Cin] (fp32, accumulated with red.add) += dy[N*Ho*Wo, Cout]^T im2col(x)
+extern "C" int b200_conv_igemm_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout,
+                                     int KH, int KW, int stride, int pad, int Ho, int Wo, int split_k, int force_bn,
+                                     cudaStream_t stream) {
+  using namespace b200;
+  const long long Mp = static_cast<long long>(N) * Ho * Wo;      // reduction length (output pixels)
+  const int Kc = KH * KW * Cin;                                    // GEMM N
+  if (Mp <= 0 || Cout <= 0) return 0;
+  if (Cin % 64 != 0 || Cout % 8 != 0 || Mp > (1ll << 30) || (reinterpret_cast<uintptr_t>(x) & 15) ||
+      (reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(dw) & 15))
+    return -2;
+  const int bn = force_bn > 0 ? force_bn : (Kc > 128 ? 256 : (Kc > 64 ? 128 : 64));
+  CUtensorMap ta, tb;
+  int rc = make_map(&ta, dy, Mp, Cout, Cout, 64, BK);              // MN-major A: rows = pixels (K), cols = Cout (M)
+  if (rc) return rc;
+  rc = b200_encode_map_im2col_bf16(&tb, x, N, H, W, Cin, KH, KW, stride, pad, 64, 64);
+  if (rc) return rc;
+  const int k_tiles = static_cast<int>((Mp + BK - 1) / BK);
+  if (split_k < 1) split_k = 1;
+  if (split_k > k_tiles) split_k = k_tiles;
+  const int per = (k_tiles + split_k - 1) / split_k;
+  split_k = (k_tiles + per - 1) / per;
+  GemmParams p;
+  p.M = Cout; p.N = Kc; p.K = static_cast<int>(Mp); p.D = dw; p.ldd = Kc; p.bias = nullptr; p.out_fp32 = 1; p.act = 0;
+  p.a_mn = 1; p.b_mn = 1; p.k_tiles_per_split = per; p.cluster_k = 1; p.atomic_out = 1;
+  p.epi_staged = 0; p.col_stats = nullptr;
+  p.tile_flags = nullptr; p.flag_epoch = 0; p.alpha = 1.0f; p.flag_elem_off = 0; p.flag_tile_elems = 0; p.ldb = Kc;
+  p.flag_bias_off = -1;
+  p.batched = 0; p.batch_inner = 1; p.batch_count = 1; p.d_outer = 0; p.d_inner = 0;
+  p.stages = 4;
+  p.conv_ho = Ho; p.conv_wo = Wo; p.conv_stride = stride; p.conv_pad = pad; p.conv_kw = KW; p.conv_cin = Cin;
+  dim3 grid((Kc + bn - 1) / bn, (Cout + BM - 1) / BM, split_k);
+  if (bn == 256) return launch_fixed<256, 4, 2>(ta, tb, p, grid, stream);
+  if (bn == 128) return launch_fixed<128, 6, 2>(ta, tb, p, grid, stream);
+  return launch_fixed<64, 8, 2>(ta, tb, p, grid, stream);
 }

@@ -62,16 +62,6 @@ static int make_map_im2col(CUtensorMap* map, const void* x, int N, int H, int W,
   return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
 }
 
-// (c, w, h, n) = first channel and BASE pixel in input coordinates; (off_w, off_h) = filter tap
-__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h,
-                                                   int n, uint16_t off_w, uint16_t off_h) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
-      : "memory");
-}
-
 // probe: CTA (m_tile, k_tile) loads one [128 pixels x 64 channels] im2col tile and writes it, un-swizzled, to
 // col[M, KH*KW*C] (the explicit kernel's layout)
 __global__ void __launch_bounds__(128)
@@ -94,8 +84,7 @@ im2col_tma_probe_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* _
     const int p0 = static_cast<int>((m0 / Wo) % Ho);
     const int n0 = static_cast<int>(m0 / (static_cast<long long>(Wo) * Ho));
     mbar_expect_tx(bar, 128 * 128);
-    tma_load_im2col_4d(tile, &tm, bar, c0, q0 * stride - pad, p0 * stride - pad, n0, static_cast<uint16_t>(s),
-                       static_cast<uint16_t>(r));
+    tma_load_im2col_4d(tile, &tm, bar, c0, q0 * stride - pad, p0 * stride - pad, n0, s, r);
   }
   mbar_wait(bar, 0);
   // thread = pixel row; undo the 128 B swizzle (16-byte chunk index ^ row % 8)
@@ -112,6 +101,11 @@ im2col_tma_probe_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* _
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" int b200_encode_map_im2col_bf16(void* map, const void* x, int N, int H, int W, int C, int KH, int KW,
+                                            int stride, int pad, int channels, int pixels) {
+  return make_map_im2col(reinterpret_cast<CUtensorMap*>(map), x, N, H, W, C, KH, KW, stride, pad, channels, pixels);
+}
 
 // col[M = N*Ho*Wo, kp = KH*KW*C] via TMA im2col loads (C % 64 == 0).  Returns -2 for unsupported shapes.
 extern "C" int b200_im2col_tma_probe(const void* x, void* col, int N, int H, int W, int C, int KH, int KW, int stride,

@@ -87,6 +87,18 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
+// TMA im2col load (implicit-GEMM convolution): (c, w, h, n) = first channel and BASE pixel in input coordinates
+// (w = q*stride - pad, h = p*stride - pad), (off_w, off_h) = filter tap; the map's pixelsPerColumn output pixels
+// are walked W-fastest inside the bounding box, out-of-image taps are zero-filled
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c, int w, int h,
+                                                   int n, int off_w, int off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+      "h"(static_cast<uint16_t>(off_w)), "h"(static_cast<uint16_t>(off_h))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
                "r"(ncols)

@@ -217,6 +217,37 @@ def im2col(x: torch.Tensor, kh: int, kw: int, stride: int, pad: int) -> Tuple[to
     return col, ho, wo, kp
 
 
+def conv_igemm_fwd(x: torch.Tensor, w2d: torch.Tensor, kh: int, kw: int, stride: int, pad: int,
+                   col_stats: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+    """EXPERIMENTAL implicit-GEMM convolution forward: ``y[N*Ho*Wo, Cout]`` straight from NHWC ``x`` through TMA
+    im2col loads (no ``col`` buffer).  ``w2d``: ``[Cout, kh*kw*Cin]`` channels_last weights.  Returns ``None``
+    when the shape is not supported (Cin % 64 != 0)."""
+    n, h, w, c = x.shape
+    cout = w2d.shape[0]
+    if c % 64 or w2d.shape[1] != kh * kw * c or not x.is_contiguous() or not w2d.is_contiguous():
+        return None
+    ho, wo = conv_out_size(h, kh, stride, pad), conv_out_size(w, kw, stride, pad)
+    M, K = n * ho * wo, kh * kw * c
+    bn = pick_bn(M, cout)
+    y = torch.empty((M, cout), dtype=BF16, device=x.device)
+    ok = load().conv_igemm_fwd(x, w2d, y, kh, kw, stride, pad, ho, wo, pick_cluster_k(M, cout, K, bn), bn, col_stats)
+    return y if ok else None
+
+
+def conv_igemm_wgrad_(dy2d: torch.Tensor, x: torch.Tensor, dw2d: torch.Tensor, kh: int, kw: int, stride: int,
+                      pad: int) -> bool:
+    """EXPERIMENTAL implicit wgrad: ``dw2d[Cout, kh*kw*Cin] += dy2d^T im2col(x)`` (fp32 atomics, split over
+    pixels) without materialising ``im2col(x)``."""
+    n, h, w, c = x.shape
+    cout = dy2d.shape[1]
+    if c % 64 or not x.is_contiguous() or not dy2d.is_contiguous() or not dw2d.is_contiguous():
+        return False
+    ho, wo = conv_out_size(h, kh, stride, pad), conv_out_size(w, kw, stride, pad)
+    M, K = n * ho * wo, kh * kw * c
+    bn = pick_bn(cout, K)
+    return bool(load().conv_igemm_wgrad(dy2d, x, dw2d, cout, kh, kw, stride, pad, ho, wo, pick_split_k(cout, K, M, bn), bn))
+
+
 def col2im(col: torch.Tensor, shape: Tuple[int, int, int, int], kh: int, kw: int, stride: int, pad: int,
            ho: int, wo: int) -> torch.Tensor:
     n, h, w, c = shape

@@ -224,6 +224,9 @@ class Linear(nn.Module):
 
 
 # ================================================================================ Conv2d (NHWC, implicit GEMM)
+_CONV_IGEMM = __import__("os").environ.get("BATON_CONV_IGEMM", "0") == "1"   # opt-in until validated on hardware
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, w_bf16, kh, kw, stride, pad, anchor, stats=None):
@@ -240,11 +243,20 @@ class _ConvFn(torch.autograd.Function):
             wc = w_bf16.view(cout, kh * kw, c)[:, (kh // 2) * kw + kw // 2, :]
             y = F.gemm(col, wc, col_stats=stats)
         else:
+            y = None
+            ctx.igemm = False
             if kh == 1 and kw == 1 and stride == 1 and pad == 0 and c % 8 == 0:
                 col, ho, wo, kp = x.view(n * h * w, c), h, w, c
-            else:
-                col, ho, wo, kp = F.im2col(x, kh, kw, stride, pad)
-            y = F.gemm(col, w_bf16, col_stats=stats)
+            elif _CONV_IGEMM and c % 64 == 0:
+                # experimental: A operand gathered by TMA im2col inside the GEMM, no col buffer (backward: implicit
+                # wgrad from x itself)
+                ho, wo, kp = F.conv_out_size(h, kh, stride, pad), F.conv_out_size(w, kw, stride, pad), kh * kw * c
+                y = F.conv_igemm_fwd(x, w_bf16, kh, kw, stride, pad, col_stats=stats)
+                col, ctx.igemm = x, y is not None
+            if y is None:
+                if not (kh == 1 and kw == 1 and stride == 1 and pad == 0 and c % 8 == 0):
+                    col, ho, wo, kp = F.im2col(x, kh, kw, stride, pad)
+                y = F.gemm(col, w_bf16, col_stats=stats)
         ctx.save_for_backward(col, w_bf16)
         ctx.weight = weight
         ctx.geom = (n, h, w, c, kh, kw, stride, pad, ho, wo, kp)
@@ -282,12 +294,20 @@ class _ConvFn(torch.autograd.Function):
                 wc = w_bf16.view(cout, kh * kw, c)[:, tap, :]
                 dx = F.gemm(dy2, wc, b_mn=True).view(n, 1, 1, c)
             return dx, gw, None, None, None, None, None, None, None
+        igemm = getattr(ctx, "igemm", False)          # col IS x: the weight gradient gathers im2col(x) on the fly
         if tgt is not None:
             # the arena view is channels_last: physical [Cout, KH, KW, Cin] == [Cout, K]
             out2d = tgt.permute(0, 2, 3, 1).reshape(cout, k_true) if tgt.dim() == 4 else tgt.view(cout, k_true)
             assert out2d.data_ptr() == tgt.data_ptr(), "conv weight grad must be channels_last in the arena"
-            WGRAD.run(lambda: F.gemm(dy2, col, a_mn=True, b_mn=True, out=out2d, accumulate=True, n_valid=k_true),
-                      dy2, col)
+            if igemm:
+                WGRAD.run(lambda: F.conv_igemm_wgrad_(dy2, col, out2d, kh, kw, stride, pad), dy2, col)
+            else:
+                WGRAD.run(lambda: F.gemm(dy2, col, a_mn=True, b_mn=True, out=out2d, accumulate=True, n_valid=k_true),
+                          dy2, col)
+        elif igemm:
+            g2 = torch.zeros((cout, k_true), dtype=torch.float32, device=dy.device)
+            F.conv_igemm_wgrad_(dy2, col, g2, kh, kw, stride, pad)
+            gw = g2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
         else:
             g2 = F.gemm(dy2, col, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True, n_valid=k_true)
             gw = g2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
