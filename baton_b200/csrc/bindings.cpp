@@ -93,6 +93,20 @@ bool im2col_tma_probe(const at::Tensor& x, at::Tensor col, int64_t kh, int64_t k
   return true;
 }
 
+bool attention_bwd(const at::Tensor& qkv, const at::Tensor& dout, const at::Tensor& probs, at::Tensor dqkv, int64_t B,
+                   int64_t S, int64_t H, int64_t dh, double scale) {
+  CHECK_CUDA(qkv); CHECK_CUDA(dout); CHECK_CUDA(probs); CHECK_CUDA(dqkv);
+  TORCH_CHECK(qkv.scalar_type() == at::kBFloat16 && dout.scalar_type() == at::kBFloat16 &&
+              probs.scalar_type() == at::kBFloat16 && dqkv.scalar_type() == at::kBFloat16 && qkv.is_contiguous() &&
+              dout.is_contiguous() && probs.is_contiguous() && dqkv.is_contiguous());
+  const c10::cuda::CUDAGuard guard(qkv.device());
+  const int rc = b200_attention_bwd(cptr(qkv), cptr(dout), cptr(probs), ptr(dqkv), static_cast<int>(B), static_cast<int>(S),
+                                    static_cast<int>(H), static_cast<int>(dh), static_cast<float>(scale), cur_stream());
+  if (rc == -2) return false;
+  check(rc, "attention_bwd");
+  return true;
+}
+
 // experimental implicit-GEMM convolution; false = shape not supported (caller falls back to im2col + GEMM)
 bool conv_igemm_fwd(const at::Tensor& x, const at::Tensor& w, at::Tensor y, int64_t kh, int64_t kw, int64_t stride,
                     int64_t pad, int64_t ho, int64_t wo, int64_t cluster_k, int64_t force_bn,
@@ -485,6 +499,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.attr("MAX_RANKS") = B200_MAX_RANKS;
   m.def("gemm", &gemm);
   m.def("attention_fwd", &attention_fwd);
+  m.def("attention_bwd", &attention_bwd);
   m.def("bn_bwd_fused", &bn_bwd_fused);
   m.def("im2col_tma_probe", &im2col_tma_probe);
   m.def("conv_igemm_fwd", &conv_igemm_fwd);

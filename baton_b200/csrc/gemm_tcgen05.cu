@@ -1297,7 +1297,11 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
 //   split_k > 1 with accumulate / fp32 atomic output -> atomic split-K; split_k < 0 -> cluster split-K of
 //   size -split_k (2, 4 or 8) for any output type.
 // Returns 0 on success, a CUDA / driver error code otherwise, -2 on unsupported alignment.
-// tensor-map encoder for other translation units (attention.cu)
+// tensor-map encoders for other translation units (attention.cu)
+extern "C" int b200_encode_map2_bf16(void* map, const void* base, long long rows, long long cols, long long ld,
+                                     int box_cols, int box_rows) {
+  return b200::make_map(reinterpret_cast<CUtensorMap*>(map), base, rows, cols, ld, box_cols, box_rows);
+}
 extern "C" int b200_encode_map4_bf16(void* map, const void* base, long long rows, long long cols, long long ld,
                                      long long inner, long long s_inner, long long outer, long long s_outer,
                                      int box_cols, int box_rows) {

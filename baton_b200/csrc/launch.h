@@ -21,6 +21,8 @@ int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int M, int N, 
 // ---- attention.cu (experimental fused attention forward, S = 128, d_head = 64)
 int b200_attention_fwd(const void* qkv, void* out, void* probs, int B, int S, int H, int dh, float scale,
                        cudaStream_t stream);
+int b200_attention_bwd(const void* qkv, const void* dout, const void* probs, void* dqkv, int B, int S, int H, int dh,
+                       float scale, cudaStream_t stream);
 // ---- implicit-GEMM convolution (experimental: gemm_tcgen05.cu CONV modes fed by TMA im2col maps)
 int b200_conv_igemm_fwd(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                         int stride, int pad, int Ho, int Wo, int cluster_k, int force_bn, float* col_stats,

@@ -680,8 +680,12 @@ class _AttnFn(torch.autograd.Function):
         B, S, H, dh = ctx.dims
         D = H * dh
         dout = dout.contiguous()
-        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         dqkv = torch.empty_like(qkv)
+        if _FUSED_ATTN and S == 128 and dh == 64:
+            # experimental single-kernel backward (csrc/attention.cu): dP / dS never leave the SM
+            if load().attention_bwd(qkv, dout, probs, dqkv, B, S, H, dh, 1.0 / math.sqrt(dh)):
+                return dqkv, None, None, None, None
+        q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         dq, dk, dv = dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:]
         bh = (H * S * S, S * S)
         pk = (S * 3 * D, dh)

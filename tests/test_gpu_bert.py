@@ -85,8 +85,8 @@ def test_bert_tiny_matches_fp32_reference_and_trains():
 
 
 @pytest.mark.skipif(os.environ.get("BATON_FUSED_ATTN") != "1",
-                    reason="experimental single-kernel attention forward: opt in with BATON_FUSED_ATTN=1")
-def test_fused_attention_forward_matches_three_kernel_path():
+                    reason="experimental single-kernel attention forward / backward: opt in with BATON_FUSED_ATTN=1")
+def test_fused_attention_forward_and_backward_match_multi_kernel_path():
     from baton_b200.ops import nn as bnn
     torch.manual_seed(0)
     dev = torch.device("cuda:0")

@@ -62,7 +62,10 @@ async def test_periodic_task_runs_and_stops():
 
     task = PeriodicTask(tick, 0.01).start()
     assert task.is_started
-    await asyncio.sleep(0.08)
+    for _ in range(600):                 # poll instead of a fixed sleep: robust on a loaded machine
+        if len(calls) >= 2:
+            break
+        await asyncio.sleep(0.005)
     await task.stop()
     n = len(calls)
     assert n >= 2
@@ -80,7 +83,10 @@ async def test_periodic_task_survives_exceptions():
         raise RuntimeError("boom")
 
     task = PeriodicTask(tick, 0.01).start()
-    await asyncio.sleep(0.06)
+    for _ in range(600):
+        if len(calls) >= 2:
+            break
+        await asyncio.sleep(0.005)
     await task.stop()
     assert len(calls) >= 2
 
