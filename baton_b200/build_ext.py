@@ -27,6 +27,8 @@ CU_SOURCES = ["gemm_tcgen05.cu", "gemm_fp8.cu", "quant.cu", "attention.cu", "im2
 HEADERS = ["ptx.cuh", "launch.h", "pdl.cuh", "mx.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
+if os.environ.get("BATON_BUILD_PHASE_TIMING") == "1":     # in-kernel %globaltimer stamps in the FedAvg collective
+    NVCC_FLAGS.append("-DB200_FEDAVG_PHASE_TIMING")
 
 
 def _nvcc() -> str:

@@ -172,12 +172,18 @@ __device__ __forceinline__ int quad_block_exponent(const float (&f)[VEC]) {
 
 // Optional in-kernel phase timestamps (multi-GPU kernels with spin barriers cannot be replayed under ncu):
 // thread 0 of the first and of the last CTA record %globaltimer at every phase boundary.
+// Compiled in only with -DB200_FEDAVG_PHASE_TIMING (BATON_BUILD_PHASE_TIMING=1 python -m baton_b200.build_ext), so
+// the default build keeps the exact instruction stream that was validated on hardware.
 __device__ __forceinline__ void phase_stamp(const FedAvgArgs& a, int slot) {
+#ifdef B200_FEDAVG_PHASE_TIMING
   if (a.phase_ns != nullptr && threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     a.phase_ns[(blockIdx.x == 0 ? 0 : 8) + slot] = t;
   }
+#else
+  (void)a; (void)slot;
+#endif
 }
 
 template <int WIRE>
