@@ -82,7 +82,9 @@ class FedAvgSession:
 
     def enable_phase_timing(self) -> None:
         """Ask the kernel to record %globaltimer at its phase boundaries (first and last CTA) -- the way to
-        see where a multi-GPU round goes, since kernels with cross-GPU spin barriers cannot run under ncu."""
+        see where a multi-GPU round goes, since kernels with cross-GPU spin barriers cannot run under ncu.
+        Needs an extension built with ``BATON_BUILD_PHASE_TIMING=1 python -m baton_b200.build_ext`` (the default
+        build compiles the stamps out, so all durations read 0)."""
         self.phase_ns = torch.zeros(16, dtype=torch.int64, device=self.device)
 
     def phase_breakdown_us(self) -> dict:
