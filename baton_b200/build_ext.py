@@ -21,7 +21,10 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "csrc", "build")
-TARGET = os.path.join(HERE, "_C.so")
+TRACE = os.environ.get("BATON_BUILD_TRACE") == "1"      # kernel-timeline build: own objects, own shared object
+if TRACE:
+    BUILD = os.path.join(HERE, "csrc", "build_trace")
+TARGET = os.path.join(HERE, "_C_trace.so" if TRACE else "_C.so")
 
 CU_SOURCES = ["gemm_tcgen05.cu", "gemm_fp8.cu", "quant.cu", "attention.cu", "im2col_tma.cu", "gemm_simt.cu", "fedavg.cu", "elementwise.cu", "conv.cu", "norm.cu", "loss.cu"]
 HEADERS = ["ptx.cuh", "launch.h", "pdl.cuh", "mx.cuh"]
@@ -29,6 +32,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "--use_fast_math", "-Xptxas", "-v"]
 if os.environ.get("BATON_BUILD_PHASE_TIMING") == "1":     # in-kernel %globaltimer stamps in the FedAvg collective
     NVCC_FLAGS.append("-DB200_FEDAVG_PHASE_TIMING")
+if TRACE:
+    NVCC_FLAGS.append("-DB200_TRACE")
 
 
 def _nvcc() -> str:

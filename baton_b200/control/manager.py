@@ -178,14 +178,22 @@ class Experiment:
             await self.pull_global()
         body = self.plane.round_start_message(self.model, update_name, n_epoch, extra)
         self._round_bytes += len(body) * len(chosen)
-        result = await self.client_manager.notify_clients(
-            "round_start", http_method="POST", data=body, clients=chosen)
-        for client_id, ok in result:
-            if ok and self.update_manager.in_progress:
+        async def _accepted(client_id: str, ok: bool) -> None:
+            # a participant joins the round the moment ITS notify returns: a fast client may finish training and
+            # POST its update while slower peers are still receiving the round (reference manager.py:87-89 only
+            # registered participants after the whole gather)
+            if ok and self.update_manager.in_progress and self.update_manager.update_name == update_name:
                 self.update_manager.client_start(client_id)
+
+        result = await self.client_manager.notify_clients(
+            "round_start", http_method="POST", data=body, clients=chosen, client_callback=_accepted)
+        if not self.update_manager.in_progress or self.update_manager.update_name != update_name:
+            return dict(result)          # every participant already reported and the round closed meanwhile
         if not self.update_manager:
             log.info("no clients working on %s; ending", update_name)
             await self.end_round()
+        elif not self.update_manager.clients_left:
+            await self.end_round()       # all updates arrived before the fan-out finished
         elif self.round_timeout:
             self._arm_timeout(update_name)
         return dict(result)
@@ -204,8 +212,16 @@ class Experiment:
                 update_name != self.update_manager.update_name):
             return web.json_response({"error": "Wrong Update"}, status=410)
         if client_id not in self.update_manager.clients:
-            # authenticated, right round, but never accepted this round's start
-            return web.json_response({"error": "Wrong Update"}, status=410)
+            sampled = (self.update_manager.update_meta or {}).get("sampled") or ()
+            if client_id not in sampled:
+                # authenticated, right round, but never asked to take part in it
+                return web.json_response({"error": "Wrong Update"}, status=410)
+            # its round_start notify has not returned yet (we are still inside the fan-out): it did accept
+            self.update_manager.client_start(client_id)
+        problem = self._validate_update(data)
+        if problem:
+            log.warning("rejecting update from %s: %s", client_id, problem)
+            return web.json_response({"error": "Bad Payload", "detail": problem}, status=400)
         self._round_bytes += len(body)
         self.update_manager.client_end(client_id, data)
         rec = self.client_manager[client_id]
@@ -214,6 +230,33 @@ class Experiment:
         if not self.update_manager.clients_left:
             await self.end_round()
         return web.json_response("OK")
+
+    def _validate_update(self, data) -> Optional[str]:
+        """Reason an update payload cannot be aggregated, or None.  A malformed upload is refused at the door
+        (400) instead of poisoning ``end_round`` for everybody else."""
+        if not isinstance(data, dict):
+            return "payload is not a mapping"
+        n = data.get("n_samples", 0)
+        if isinstance(n, bool) or not isinstance(n, (int, float)) or n != n or n in (float("inf"), float("-inf")) or n < 0:
+            return "n_samples must be a finite number >= 0"
+        hist = data.get("loss_history", [])
+        if not isinstance(hist, (list, tuple)) or any(
+                isinstance(h, bool) or not isinstance(h, (int, float)) for h in hist):
+            return "loss_history must be a list of numbers"
+        if self.plane.carries_tensors and "state_dict" in data:
+            sd = data["state_dict"]
+            if not hasattr(sd, "keys"):
+                return "state_dict is not a mapping"
+            for key, ref in self.model.state_dict().items():
+                if key not in sd:
+                    return "state_dict is missing {!r}".format(key)
+                val = sd[key]
+                if not hasattr(val, "shape") or tuple(val.shape) != tuple(ref.shape):
+                    return "state_dict[{!r}] has shape {} (expected {})".format(
+                        key, tuple(getattr(val, "shape", ())), tuple(ref.shape))
+                if ref.is_floating_point() != val.is_floating_point():
+                    return "state_dict[{!r}] has dtype {} (expected {})".format(key, val.dtype, ref.dtype)
+        return None
 
     # -- round end / aggregation --------------------------------------------
     async def trigger_end_round(self, request: web.Request) -> web.Response:
@@ -236,11 +279,18 @@ class Experiment:
             datas = dict(self.update_manager.client_responses)
             N = sum(d.get("n_samples", 0) for d in datas.values())
             aggregated = False
-            if N:
-                # the collective runs while the round is still marked open so a
-                # concurrent /start_round gets 423 instead of racing the reduce
-                aggregated = await self.plane.aggregate(self, datas)
-            self.update_manager.end_update()
+            try:
+                if N:
+                    # the collective runs while the round is still marked open so a
+                    # concurrent /start_round gets 423 instead of racing the reduce
+                    aggregated = await self.plane.aggregate(self, datas)
+            except Exception:
+                # a failed reduce must not wedge the experiment: the planes commit atomically, so the global
+                # model is untouched; the round is closed (lock released) and reported as not aggregated
+                log.exception("aggregation of %s failed; global model left unchanged", update_name)
+                aggregated = False
+            finally:
+                self.update_manager.end_update()
             if not N:
                 log.info("no responses for %s", update_name)
                 self.metrics.add(update_name=update_name, n_clients=0, n_samples=0,

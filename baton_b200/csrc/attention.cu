@@ -14,6 +14,7 @@
 // The S x S scores never touch HBM and P is written exactly once (the unfused path writes S, reads S,
 // writes P, reads P).  EXPERIMENTAL: compiled and wired behind BATON_FUSED_ATTN=1, not yet validated on
 // hardware (round-1 GPU budget ran out) -- the default path stays the three-kernel one.
+#define B200_TU_TAG 4
 #include "launch.h"
 #include "pdl.cuh"
 #include "ptx.cuh"
@@ -469,3 +470,5 @@ extern "C" int b200_attention_bwd(const void* qkv, const void* dout, const void*
   if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
+
+B200_TRACE_REGISTER(attention)

@@ -24,6 +24,30 @@ inline T* opt_ptr(const std::optional<at::Tensor>& t) {
 }
 #define CHECK_CUDA(x) TORCH_CHECK((x).is_cuda(), #x " must be a CUDA tensor")
 
+// ---- in-graph kernel timeline (pdl.cuh): every translation unit owns a copy of the trace pointer
+extern "C" {
+#define B200_TRACE_TUS(X) X(gemm_tcgen05) X(gemm_fp8) X(quant) X(attention) X(im2col_tma) X(gemm_simt) X(fedavg) \
+  X(elementwise) X(conv) X(norm) X(loss)
+#define B200_DECL(tu) int b200_trace_set_##tu(unsigned long long* p);
+B200_TRACE_TUS(B200_DECL)
+#undef B200_DECL
+}
+// buf: int64 CUDA tensor [2 + 2 * capacity] ({cursor, capacity, (t_ns, tag)...}) or None to stop tracing.
+// Returns false when the extension was not built with -DB200_TRACE.
+bool trace_set(const std::optional<at::Tensor>& buf) {
+  unsigned long long* p = nullptr;
+  if (buf.has_value() && buf->defined()) {
+    CHECK_CUDA(*buf);
+    TORCH_CHECK(buf->scalar_type() == at::kLong && buf->is_contiguous() && buf->numel() >= 4, "trace buffer: int64 [2+2n]");
+    p = reinterpret_cast<unsigned long long*>(buf->data_ptr());
+  }
+  int rc = 0;
+#define B200_SET(tu) rc |= b200_trace_set_##tu(p);
+  B200_TRACE_TUS(B200_SET)
+#undef B200_SET
+  return rc == 0;
+}
+
 void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::optional<at::Tensor>& bias, int64_t M,
           int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd, bool a_mn, bool b_mn, int64_t act,
           int64_t split_k, bool accumulate, double alpha, const std::optional<at::Tensor>& flags, int64_t flag_epoch,
@@ -123,6 +147,22 @@ bool conv_igemm_fwd(const at::Tensor& x, const at::Tensor& w, at::Tensor y, int6
                                      cur_stream());
   if (rc == -2) return false;
   check(rc, "conv_igemm_fwd");
+  return true;
+}
+// dx [N, H, W, Cin] = implicit dgrad of a stride-1 convolution; dy [N, Ho, Wo, Cout], w [Cout, KH*KW*Cin]
+bool conv_igemm_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor dx, int64_t kh, int64_t kw, int64_t pad,
+                      int64_t cluster_k, int64_t force_bn) {
+  CHECK_CUDA(dy); CHECK_CUDA(w); CHECK_CUDA(dx);
+  TORCH_CHECK(dy.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && dx.scalar_type() == at::kBFloat16 &&
+              dy.dim() == 4 && dx.dim() == 4 && dy.is_contiguous() && w.is_contiguous() && dx.is_contiguous());
+  const c10::cuda::CUDAGuard guard(dy.device());
+  const int rc = b200_conv_igemm_dgrad(cptr(dy), cptr(w), ptr(dx), static_cast<int>(dx.size(0)), static_cast<int>(dx.size(1)),
+                                       static_cast<int>(dx.size(2)), static_cast<int>(dx.size(3)), static_cast<int>(dy.size(3)),
+                                       static_cast<int>(kh), static_cast<int>(kw), static_cast<int>(pad),
+                                       static_cast<int>(dy.size(1)), static_cast<int>(dy.size(2)),
+                                       static_cast<int>(cluster_k), static_cast<int>(force_bn), cur_stream());
+  if (rc == -2) return false;
+  check(rc, "conv_igemm_dgrad");
   return true;
 }
 bool conv_igemm_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor dw, int64_t cout, int64_t kh, int64_t kw,
@@ -498,12 +538,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "baton_b200 sm_100a kernels";
   m.attr("MAX_RANKS") = B200_MAX_RANKS;
   m.def("gemm", &gemm);
+  m.def("trace_set", &trace_set);
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd);
   m.def("bn_bwd_fused", &bn_bwd_fused);
   m.def("im2col_tma_probe", &im2col_tma_probe);
   m.def("conv_igemm_fwd", &conv_igemm_fwd);
   m.def("conv_igemm_wgrad", &conv_igemm_wgrad);
+  m.def("conv_igemm_dgrad", &conv_igemm_dgrad);
   m.def("gemm_batched", &gemm_batched);
   m.def("gemm_fp8", &gemm_fp8);
   m.def("quant_mx_rows", &quant_mx_rows);

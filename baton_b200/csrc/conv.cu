@@ -2,6 +2,7 @@
 // (dgrad scatter written as a gather so it needs no atomics), max / average pooling.
 // A convolution is   Y[N*Ho*Wo, Cout] = col[N*Ho*Wo, KH*KW*Cin] * W[Cout, KH*KW*Cin]^T
 // with K index = (kh*KW + kw)*Cin + c, i.e. weights stored [Cout, KH, KW, Cin] (channels_last).
+#define B200_TU_TAG 9
 #include "launch.h"
 #include "pdl.cuh"
 #include "ptx.cuh"
@@ -296,3 +297,5 @@ extern "C" int b200_avgpool_bwd_nhwc(const void* dy, void* dx, int N, int HW, in
                                                                 reinterpret_cast<__nv_bfloat16*>(dx), N, HW, C);
   RET_LAST();
 }
+
+B200_TRACE_REGISTER(conv)

@@ -2,6 +2,7 @@
 // weighted sum (manager-side FedAvg, K1 fallback), casts, batch row gather (K8), column sums
 // (bias gradients), ReLU / GELU pieces.  All use 16-byte vectors and grid-stride loops sized to
 // 148 SMs x a few resident CTAs.
+#define B200_TU_TAG 8
 #include "launch.h"
 #include "pdl.cuh"
 #include "ptx.cuh"
@@ -508,3 +509,5 @@ extern "C" int b200_embedding_bwd(const void* dy, const long long* idx, float* g
              reinterpret_cast<const uint4*>(dy), idx, grad, n_rows, width / 8);
   RET_LAST();
 }
+
+B200_TRACE_REGISTER(elementwise)

@@ -31,6 +31,8 @@
 // alive_mask bit k == 0 -> rank k is neither read, written nor waited for (dead process), so a
 // dead peer cannot hang the collective the way a blocking NCCL call would; a bounded spin turns a
 // peer that dies mid-collective into an error status instead of a hang.
+#define B200_TU_TAG 7
+#include "pdl.cuh"
 #include "ptx.cuh"
 #include "launch.h"
 #include "mx.cuh"
@@ -509,3 +511,5 @@ extern "C" int b200_flag_barrier(unsigned long long* const* pads, int rank, int 
   flag_barrier_kernel<<<1, 32, 0, stream>>>(a, slot);
   return static_cast<int>(cudaGetLastError());
 }
+
+B200_TRACE_REGISTER(fedavg)

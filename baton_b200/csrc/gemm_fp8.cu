@@ -18,6 +18,7 @@
 //
 // `block_scaled = 0` runs the same pipeline with `kind::f8f6f4` (no scale factors; per-tensor scales
 // folded into alpha).
+#define B200_TU_TAG 2
 #include "ptx.cuh"
 #include "launch.h"
 #include "pdl.cuh"
@@ -346,3 +347,5 @@ extern "C" int b200_gemm_fp8(const void* a, const void* b, void* d, const float*
   if (bn == 128) return launch8<128, 5>(ta, tb, p, grid, stream);
   return launch8<64, 6>(ta, tb, p, grid, stream);
 }
+
+B200_TRACE_REGISTER(gemm_fp8)

@@ -1,6 +1,7 @@
 // CUDA-core fallback GEMM for shapes the TMA path cannot take (row pitch not a multiple of 16
 // bytes, e.g. the 10-class classifier head) -- tiny problems only.  Same contract as
 // b200_gemm_bf16: D = act(alpha * A B^T + bias) with K-major or MN-major bf16 operands.
+#define B200_TU_TAG 6
 #include "launch.h"
 #include "pdl.cuh"
 #include <cuda_bf16.h>
@@ -89,3 +90,5 @@ extern "C" int b200_gemm_simt(const void* a, const void* b, void* d, const float
       ldb, ldd, a_mn, b_mn, out_fp32, act, accumulate, alpha);
   return static_cast<int>(cudaGetLastError());
 }
+
+B200_TRACE_REGISTER(gemm_simt)

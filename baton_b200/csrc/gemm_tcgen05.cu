@@ -26,6 +26,7 @@
 // arrival flags (published by the FedAvg kernel with st.release) before issuing the TMA loads of
 // a weight tile, so the first GEMM of a round consumes the new global weights tile by tile while
 // the rest of the model is still landing over NVLink.
+#define B200_TU_TAG 1
 #include "ptx.cuh"
 #include "launch.h"
 #include "pdl.cuh"
@@ -68,7 +69,9 @@ struct GemmParams {
   int conv_ho, conv_wo;    // output image size
   int conv_stride, conv_pad;
   int conv_kw;             // filter width (tap = r * kw + s)
-  int conv_cin;            // input channels (multiple of 64)
+  int conv_cin;            // channels of the im2col-gathered tensor (multiple of 64): Cin forward, Cout for dgrad
+  int conv_taps;           // dgrad: KH * KW
+  int conv_ncol;           // dgrad: Cin of the convolution (column pitch of one tap inside a weight row)
 };
 
 template <int BN>
@@ -235,7 +238,10 @@ __device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, in
 // ---- fixed-depth pipeline, one CTA per SM: the default path ----
 // CONV: 0 = plain GEMM; 1 = implicit-GEMM conv forward (A = im2col(x) gathered by TMA im2col, k-tile = one filter
 // tap x 64 input channels); 2 = implicit wgrad (B = im2col(x) MN-major, k-tile = 64 output pixels, every 64-wide
-// N atom = one tap x 64 channels).  EXPERIMENTAL modes, see csrc/im2col_tma.cu.
+// N atom = one tap x 64 channels); 3 = implicit dgrad of a stride-1 convolution: dx = conv(dy, flipped w) -- A =
+// im2col(dy) gathered by TMA im2col with pad' = k - 1 - pad (k-tile = one flipped tap x 64 OUTPUT channels), B = the
+// [64 cout] x [BN cin] slab of that tap inside the channels_last weight matrix, loaded MN-major (no weight transpose,
+// no col2im).  See csrc/im2col_tma.cu for the tensor maps.
 template <int BN, int STAGES, int CONV = 0>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -334,7 +340,7 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               tma_load_4d(sb + j * 8192, &tmB, &full_bar[s], n0 + j * 64, k0, bz_inner, bz_outer);
           }
         } else {
-        if constexpr (CONV == 1) {
+        if constexpr (CONV == 1 || CONV == 3) {
           // k-tile -> (filter tap, 64-channel block); base pixel of this CTA's 128 output pixels in input coords
           const int kt = kt_begin + i;
           const int cblocks = p.conv_cin >> 6;
@@ -364,6 +370,13 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               tma_load_im2col_4d(sb + j * 8192, &tmB, &full_bar[s], c, w0, h0, img, fs, fr);
             }
           }
+        } else if constexpr (CONV == 3) {
+          const int kt = kt_begin + i;
+          const int cblocks = p.conv_cin >> 6;
+          const int tap = kt / cblocks, cb = kt - tap * cblocks;
+          const int wcol = (p.conv_taps - 1 - tap) * p.conv_ncol + n0;      // flipped tap, cin block of this CTA
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], wcol + j * 64, cb * 64);
         } else if (!p.b_mn) {
           tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box [64 k][BN rows]
         } else {
@@ -964,7 +977,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         uint8_t* sb = sa + L::A_BYTES;
         const int k0 = (kt_begin + i) * BK;
         mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        if constexpr (CONV == 1) {
+        if constexpr (CONV == 1 || CONV == 3) {
           const int kt = kt_begin + i;
           const int cblocks = p.conv_cin >> 6;
           const int tap = kt / cblocks, cb = kt - tap * cblocks;
@@ -979,7 +992,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < BM / 64; ++j)  // box [64 m][64 k rows] per MN atom
             tma_load_2d(sa + j * 8192, &tmA, &full_bar[s], m0 + j * 64, k0);
         }
-        if (!p.b_mn) {
+        if constexpr (CONV == 3) {
+          const int kt = kt_begin + i;
+          const int cblocks = p.conv_cin >> 6;
+          const int tap = kt / cblocks, cb = kt - tap * cblocks;
+          const int wcol = (p.conv_taps - 1 - tap) * p.conv_ncol + n0;
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, &full_bar[s], wcol + j * 64, cb * 64);
+        } else if (!p.b_mn) {
           tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);  // box [64 k][BN rows]
         } else {
 #pragma unroll
@@ -1501,6 +1521,7 @@ extern "C" int b200_conv_igemm_fwd(const void* x, const void* w, void* y, int N,
   const int max_stages = (bn == 256) ? 4 : (bn == 128 ? 6 : 8);
   p.stages = per < max_stages ? (per < 2 ? 2 : per) : max_stages;
   p.conv_ho = Ho; p.conv_wo = Wo; p.conv_stride = stride; p.conv_pad = pad; p.conv_kw = KW; p.conv_cin = Cin;
+  p.conv_taps = KH * KW; p.conv_ncol = Cin;
   dim3 grid((Cout + bn - 1) / bn, static_cast<unsigned>((M + BM - 1) / BM), cluster_k);
   if (cluster_k > 1) {
     if (bn == 256) return launch_cfg<256, 1>(ta, tb, p, grid, stream);
@@ -1510,6 +1531,54 @@ extern "C" int b200_conv_igemm_fwd(const void* x, const void* w, void* y, int N,
   if (bn == 256) return launch_fixed<256, 4, 1>(ta, tb, p, grid, stream);
   if (bn == 128) return launch_fixed<128, 6, 1>(ta, tb, p, grid, stream);
   return launch_fixed<64, 8, 1>(ta, tb, p, grid, stream);
+}
+
+// input gradient of a STRIDE-1 convolution: dx[N*H*W, Cin] = im2col_{pad' = K-1-pad}(dy) * flip(w), dy NHWC bf16
+// [N, Ho, Wo, Cout] (Cout % 64 == 0), w [Cout, KH*KW*Cin] channels_last (Cin % 64 == 0 so that a 64-wide N atom never
+// straddles two taps).  No col buffer, no col2im, no weight transpose.
+extern "C" int b200_conv_igemm_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout,
+                                     int KH, int KW, int pad, int Ho, int Wo, int cluster_k, int force_bn,
+                                     cudaStream_t stream) {
+  using namespace b200;
+  const long long M = static_cast<long long>(N) * H * W;
+  const int K = KH * KW * Cout;
+  if (M <= 0 || Cin <= 0) return 0;
+  const int padp = KH - 1 - pad, padq = KW - 1 - pad;
+  if (Cout % 64 != 0 || Cin % 64 != 0 || M > (1ll << 30) || padp < 0 || padq < 0 || padp != padq ||
+      Ho + 2 * padp - (KH - 1) != H || Wo + 2 * padq - (KW - 1) != W || (reinterpret_cast<uintptr_t>(dy) & 15) ||
+      (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(dx) & 15))
+    return -2;
+  const int bn = force_bn > 0 ? force_bn : (Cin > 128 ? 256 : (Cin > 64 ? 128 : 64));
+  CUtensorMap ta, tb;
+  int rc = b200_encode_map_im2col_bf16(&ta, dy, N, Ho, Wo, Cout, KH, KW, 1, padp, 64, BM);
+  if (rc) return rc;
+  rc = make_map(&tb, w, Cout, static_cast<long long>(KH) * KW * Cin, static_cast<long long>(KH) * KW * Cin, 64, BK);
+  if (rc) return rc;
+  const int k_tiles = K / BK;
+  if (cluster_k != 1 && cluster_k != 2 && cluster_k != 4 && cluster_k != 8) return -5;
+  while (cluster_k > 1 && (cluster_k - 1) * ((k_tiles + cluster_k - 1) / cluster_k) >= k_tiles) cluster_k >>= 1;
+  const int per = (k_tiles + cluster_k - 1) / cluster_k;
+  GemmParams p;
+  p.M = static_cast<int>(M); p.N = Cin; p.K = K; p.D = dx; p.ldd = Cin; p.bias = nullptr; p.out_fp32 = 0; p.act = 0;
+  p.a_mn = 0; p.b_mn = 1; p.k_tiles_per_split = per; p.cluster_k = cluster_k; p.atomic_out = 0;
+  p.epi_staged = 0; p.col_stats = nullptr;
+  p.tile_flags = nullptr; p.flag_epoch = 0; p.alpha = 1.0f; p.flag_elem_off = 0; p.flag_tile_elems = 0;
+  p.ldb = static_cast<long long>(KH) * KW * Cin;
+  p.flag_bias_off = -1;
+  p.batched = 0; p.batch_inner = 1; p.batch_count = 1; p.d_outer = 0; p.d_inner = 0;
+  const int max_stages = (bn == 256) ? 4 : (bn == 128 ? 6 : 8);
+  p.stages = per < max_stages ? (per < 2 ? 2 : per) : max_stages;
+  p.conv_ho = H; p.conv_wo = W; p.conv_stride = 1; p.conv_pad = padp; p.conv_kw = KW; p.conv_cin = Cout;
+  p.conv_taps = KH * KW; p.conv_ncol = Cin;
+  dim3 grid((Cin + bn - 1) / bn, static_cast<unsigned>((M + BM - 1) / BM), cluster_k);
+  if (cluster_k > 1) {
+    if (bn == 256) return launch_cfg<256, 3>(ta, tb, p, grid, stream);
+    if (bn == 128) return launch_cfg<128, 3>(ta, tb, p, grid, stream);
+    return launch_cfg<64, 3>(ta, tb, p, grid, stream);
+  }
+  if (bn == 256) return launch_fixed<256, 4, 3>(ta, tb, p, grid, stream);
+  if (bn == 128) return launch_fixed<128, 6, 3>(ta, tb, p, grid, stream);
+  return launch_fixed<64, 8, 3>(ta, tb, p, grid, stream);
 }
 
 // weight gradient: dw[Cout, KH*KW*Cin] (fp32, accumulated with red.add) += dy[N*Ho*Wo, Cout]^T im2col(x)
@@ -1543,8 +1612,11 @@ extern "C" int b200_conv_igemm_wgrad(const void* dy, const void* x, float* dw, i
   p.batched = 0; p.batch_inner = 1; p.batch_count = 1; p.d_outer = 0; p.d_inner = 0;
   p.stages = 4;
   p.conv_ho = Ho; p.conv_wo = Wo; p.conv_stride = stride; p.conv_pad = pad; p.conv_kw = KW; p.conv_cin = Cin;
+  p.conv_taps = KH * KW; p.conv_ncol = Cin;
   dim3 grid((Kc + bn - 1) / bn, (Cout + BM - 1) / BM, split_k);
   if (bn == 256) return launch_fixed<256, 4, 2>(ta, tb, p, grid, stream);
   if (bn == 128) return launch_fixed<128, 6, 2>(ta, tb, p, grid, stream);
   return launch_fixed<64, 8, 2>(ta, tb, p, grid, stream);
 }
+
+B200_TRACE_REGISTER(gemm_tcgen05)

@@ -14,6 +14,7 @@
 // memory in the layout of the explicit im2col kernel, so the semantics can be pinned down against it
 // (tests/test_gpu_kernels.py::test_tma_im2col_probe_matches_explicit_im2col, opt-in: BATON_TMA_IM2COL=1).
 // EXPERIMENTAL: written after the round-1 GPU budget ran out, never run on hardware, not used by any model path.
+#define B200_TU_TAG 5
 #include <cuda.h>
 
 #include "launch.h"
@@ -122,3 +123,5 @@ extern "C" int b200_im2col_tma_probe(const void* x, void* col, int N, int H, int
                                                                         stride, pad, Ho, Wo, M, kp);
   return static_cast<int>(cudaGetLastError());
 }
+
+B200_TRACE_REGISTER(im2col_tma)

@@ -27,6 +27,8 @@ int b200_attention_bwd(const void* qkv, const void* dout, const void* probs, voi
 int b200_conv_igemm_fwd(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                         int stride, int pad, int Ho, int Wo, int cluster_k, int force_bn, float* col_stats,
                         cudaStream_t stream);
+int b200_conv_igemm_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                          int pad, int Ho, int Wo, int cluster_k, int force_bn, cudaStream_t stream);
 int b200_conv_igemm_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                           int stride, int pad, int Ho, int Wo, int split_k, int force_bn, cudaStream_t stream);
 // ---- im2col_tma.cu (experimental: TMA im2col tensor maps, probe kernel only)

@@ -1,6 +1,7 @@
 // Fused loss kernels (K7): forward + backward in one pass, with the batch-mean loss accumulated
 // into a device scalar that the trainer reads ONCE per epoch (the reference does float(loss) -- a
 // host sync -- on every batch: utils.py:88).
+#define B200_TU_TAG 11
 #include "launch.h"
 #include "pdl.cuh"
 #include "ptx.cuh"
@@ -144,3 +145,5 @@ extern "C" int b200_mse(const void* pred, int pred_fp32, const float* target, vo
 #undef MSE
   return static_cast<int>(cudaGetLastError());
 }
+
+B200_TRACE_REGISTER(loss)

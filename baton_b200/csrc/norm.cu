@@ -1,6 +1,7 @@
 // Normalisation kernels (K6): BatchNorm forward/backward over NHWC activations viewed as a
 // [rows, C] bf16 matrix (fused residual add + ReLU, running-stat update), LayerNorm forward /
 // backward (fused residual add) and row softmax for attention.  Statistics and gradients in fp32.
+#define B200_TU_TAG 10
 #include "launch.h"
 #include "pdl.cuh"
 #include "ptx.cuh"
@@ -1061,3 +1062,5 @@ extern "C" int b200_softmax_bwd(const void* y, const void* dy, void* dx, long lo
   launch_pdl(softmax_bwd_kernel, static_cast<unsigned>((rows + 7) / 8), 256, 0, stream, yp, gp, dp, rows, C, scale);
   RET_LAST();
 }
+
+B200_TRACE_REGISTER(norm)

@@ -17,10 +17,53 @@
 
 namespace b200 {
 
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch_dependents() {
+// ---- in-graph kernel timeline (build with -DB200_TRACE: `BATON_BUILD_TRACE=1 python -m baton_b200.build_ext`) ----
+// CUDA graphs hide per-kernel timing from CUDA events, and ncu serialises launches with cold caches, so neither
+// shows where a captured local-SGD step spends its time.  In a trace build CTA 0 of every kernel stamps
+// %globaltimer twice: when it becomes resident (tag < 0, at griddep_launch_dependents) and when its
+// dependencies have completed (tag > 0, after griddep_wait).  tag = TU id * 100000 + source line, resolved back
+// to the kernel name by baton_b200/utils/trace.py.  The buffer pointer lives in a per-translation-unit
+// __device__ variable (no relocatable device code), set through b200_trace_set_<tu>().
+#ifndef B200_TU_TAG
+#define B200_TU_TAG 0
+#endif
+#ifdef B200_TRACE
+static __device__ unsigned long long* b200_trace_ptr = nullptr;   // [0] = cursor, [1] = capacity, then (t, tag) pairs
+__device__ __forceinline__ void trace_stamp(long long tag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long* p = b200_trace_ptr;
+    if (p != nullptr) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      const unsigned long long i = atomicAdd(p, 1ull);
+      if (i < p[1]) {
+        p[2 + 2 * i] = t;
+        p[3 + 2 * i] = static_cast<unsigned long long>(tag);
+      }
+    }
+  }
+}
+static int b200_trace_set_local(unsigned long long* p) {
+  return static_cast<int>(cudaMemcpyToSymbol(b200_trace_ptr, &p, sizeof(p)));
+}
+#define B200_TRACE_REGISTER(tu) \
+  extern "C" int b200_trace_set_##tu(unsigned long long* p) { return b200::b200_trace_set_local(p); }
+#else
+__device__ __forceinline__ void trace_stamp(long long) {}
+#define B200_TRACE_REGISTER(tu) \
+  extern "C" int b200_trace_set_##tu(unsigned long long*) { return -1; }
+#endif
+
+__device__ __forceinline__ void griddep_wait_tagged(long long tag) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  trace_stamp(tag);
+}
+__device__ __forceinline__ void griddep_launch_dependents_tagged(long long tag) {
+  trace_stamp(-tag);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+#define griddep_wait() griddep_wait_tagged(static_cast<long long>(B200_TU_TAG) * 100000 + __LINE__)
+#define griddep_launch_dependents() griddep_launch_dependents_tagged(static_cast<long long>(B200_TU_TAG) * 100000 + __LINE__)
 
 inline bool pdl_enabled() {
   static int on = -1;

@@ -8,6 +8,7 @@
 //
 // Scales are written directly in the 512-byte atom layout tcgen05 consumes (gemm_fp8.cu):
 //   atom(row_tile, k_tile)[ (row % 32) * 16 + ((row % 128) / 32) * 4 + (k % 128) / 32 ]
+#define B200_TU_TAG 3
 #include <cuda_fp8.h>
 
 #include "launch.h"
@@ -153,3 +154,5 @@ extern "C" int b200_dequant_mx(const void* q, const void* sf, float* out, long l
       reinterpret_cast<const uint8_t*>(q), reinterpret_cast<const uint8_t*>(sf), out, R, C, Cp, Cpad);
   return static_cast<int>(cudaGetLastError());
 }
+
+B200_TRACE_REGISTER(quant)

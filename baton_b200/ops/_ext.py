@@ -56,7 +56,16 @@ def load(build_if_missing: bool = False):
         from .. import build_ext
         build_ext.build()
     try:
-        _RAW = importlib.import_module("baton_b200._C")
+        if os.environ.get("BATON_TRACE") == "1":
+            # kernel-timeline build (BATON_BUILD_TRACE=1 python -m baton_b200.build_ext): same module, -DB200_TRACE
+            from importlib import machinery, util
+            path = os.path.join(here, "_C_trace.so")
+            loader = machinery.ExtensionFileLoader("_C", path)
+            spec = util.spec_from_file_location("_C", path, loader=loader)
+            _RAW = util.module_from_spec(spec)
+            loader.exec_module(_RAW)
+        else:
+            _RAW = importlib.import_module("baton_b200._C")
     except Exception as exc:  # pragma: no cover - exercised only on broken installs
         raise RuntimeError(
             "baton_b200._C (sm_100a kernels) is not available: {!r}. "

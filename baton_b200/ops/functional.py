@@ -234,6 +234,22 @@ def conv_igemm_fwd(x: torch.Tensor, w2d: torch.Tensor, kh: int, kw: int, stride:
     return y if ok else None
 
 
+def conv_igemm_dgrad(dy: torch.Tensor, w2d: torch.Tensor, in_shape, kh: int, kw: int, pad: int) -> Optional[torch.Tensor]:
+    """Implicit-GEMM input gradient of a STRIDE-1 convolution: ``dx[N, H, W, Cin]`` from NHWC ``dy`` and the
+    channels_last weights ``w2d [Cout, kh*kw*Cin]`` -- the flipped-filter convolution of ``dy``, gathered by TMA
+    im2col, with the weight slab of each tap loaded MN-major in place (no ``dcol`` buffer, no col2im, no weight
+    transpose).  Returns ``None`` when the shape is not supported (channels not multiples of 64)."""
+    n, h, w, c = in_shape
+    cout = dy.shape[-1]
+    if c % 64 or cout % 64 or w2d.shape[1] != kh * kw * c or not dy.is_contiguous() or not w2d.is_contiguous():
+        return None
+    M, K = n * h * w, kh * kw * cout
+    bn = pick_bn(M, c)
+    dx = torch.empty((n, h, w, c), dtype=BF16, device=dy.device)
+    ok = load().conv_igemm_dgrad(dy, w2d, dx, kh, kw, pad, pick_cluster_k(M, c, K, bn), bn)
+    return dx if ok else None
+
+
 def conv_igemm_wgrad_(dy2d: torch.Tensor, x: torch.Tensor, dw2d: torch.Tensor, kh: int, kw: int, stride: int,
                       pad: int) -> bool:
     """EXPERIMENTAL implicit wgrad: ``dw2d[Cout, kh*kw*Cin] += dy2d^T im2col(x)`` (fp32 atomics, split over

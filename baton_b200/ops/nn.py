@@ -224,7 +224,10 @@ class Linear(nn.Module):
 
 
 # ================================================================================ Conv2d (NHWC, implicit GEMM)
-_CONV_IGEMM = __import__("os").environ.get("BATON_CONV_IGEMM", "0") == "1"   # opt-in until validated on hardware
+# implicit-GEMM convolution (TMA im2col operands; validated on B200 in round 2, profiles/r2_validate_experimental.txt).
+# BATON_CONV_IGEMM=0 falls back to explicit im2col / col2im + GEMM.
+_CONV_IGEMM = __import__("os").environ.get("BATON_CONV_IGEMM", "1") == "1"
+_CONV_IGEMM_DGRAD = __import__("os").environ.get("BATON_CONV_IGEMM_DGRAD", "1") == "1"
 
 
 class _ConvFn(torch.autograd.Function):
@@ -313,11 +316,16 @@ class _ConvFn(torch.autograd.Function):
             gw = g2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
         dx = None
         if ctx.needs_dx:
-            dcol = F.gemm(dy2, w_bf16, b_mn=True)  # [M, kp]
-            if kh == 1 and kw == 1 and stride == 1 and pad == 0 and c % 8 == 0:
-                dx = dcol.view(n, h, w, c)
-            else:
-                dx = F.col2im(dcol, (n, h, w, c), kh, kw, stride, pad, ho, wo)
+            if (_CONV_IGEMM and _CONV_IGEMM_DGRAD and stride == 1 and kh == kw and kh > 1 and kp == k_true
+                    and w_bf16.shape[1] == k_true):
+                # implicit dgrad: flipped-filter convolution of dy, no dcol buffer / col2im
+                dx = F.conv_igemm_dgrad(dy2.view(n, ho, wo, cout), w_bf16, (n, h, w, c), kh, kw, pad)
+            if dx is None:
+                dcol = F.gemm(dy2, w_bf16, b_mn=True)  # [M, kp]
+                if kh == 1 and kw == 1 and stride == 1 and pad == 0 and c % 8 == 0:
+                    dx = dcol.view(n, h, w, c)
+                else:
+                    dx = F.col2im(dcol, (n, h, w, c), kh, kw, stride, pad, ho, wo)
         return dx, gw, None, None, None, None, None, None, None
 
 

@@ -74,10 +74,17 @@ class HttpManagerPlane(ManagerPlane):
         datas = [d for d in responses.values() if "state_dict" in d]
         if not datas:
             return False
-        return fedavg_into(experiment.model.state_dict(),
-                           [d["state_dict"] for d in datas],
-                           [d["n_samples"] for d in datas],
-                           int_policy=self.int_policy)
+        # reduce into a scratch copy and commit only when every key went through: a client payload that makes
+        # the reduce raise half-way must not leave the global model half-written
+        live = experiment.model.state_dict()
+        scratch = type(live)((k, v.detach().clone()) for k, v in live.items())
+        ok = fedavg_into(scratch, [d["state_dict"] for d in datas], [d["n_samples"] for d in datas],
+                         int_policy=self.int_policy)
+        if ok:
+            with torch.no_grad():
+                for k, v in live.items():
+                    v.copy_(scratch[k])
+        return ok
 
 
 class SeatedManagerPlane(ManagerPlane):

@@ -11,7 +11,12 @@ reach the port (quirk 9).  The schemas are kept:
 
 but decoding goes through an allow-listing unpickler that only rebuilds
 tensors, containers and scalars, so a stock reference peer's payload still
-loads while ``os.system`` gadgets do not.  Messages that carry no tensors (the
+loads while ``os.system`` gadgets do not.  ``torch.storage._load_from_bytes``
+(what a pickled tensor's storage reduces to) is itself ``torch.load(...,
+weights_only=False)``, i.e. a second, unrestricted pickle nested inside the
+payload; it is therefore NOT resolved to the torch function but to
+:func:`_safe_load_from_bytes`, which decodes the nested stream with
+``weights_only=True``.  Messages that carry no tensors (the
 fused NVLink data plane moves tensors GPU-to-GPU) are plain JSON.
 """
 from __future__ import annotations
@@ -50,8 +55,20 @@ class UnsafePayload(pickle.UnpicklingError):
     pass
 
 
+def _safe_load_from_bytes(b):
+    """Replacement for ``torch.storage._load_from_bytes``: the nested storage stream is itself a pickle, so it
+    goes through torch's restricted ``weights_only`` unpickler instead of the stock unrestricted one."""
+    import torch
+    try:
+        return torch.load(io.BytesIO(b), weights_only=True)
+    except pickle.UnpicklingError as exc:
+        raise UnsafePayload("nested storage payload rejected: {}".format(exc)) from exc
+
+
 class _TensorUnpickler(pickle.Unpickler):
     def find_class(self, module: str, name: str):
+        if (module, name) == ("torch.storage", "_load_from_bytes"):
+            return _safe_load_from_bytes
         if (module, name) in _ALLOWED or name in _ALLOWED_PREFIX_ATTRS.get(module, ()):
             return super().find_class(module, name)
         raise UnsafePayload("refusing to unpickle {}.{}".format(module, name))

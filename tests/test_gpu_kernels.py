@@ -195,8 +195,6 @@ def test_conv_bn_fused_statistics_match_separate_pass(bnn):
     assert _rel(g1, g0) < 2e-2
 
 
-@pytest.mark.skipif(os.environ.get("BATON_TMA_IM2COL") != "1",
-                    reason="experimental TMA im2col probe (implicit-GEMM ground work): opt in with BATON_TMA_IM2COL=1")
 @pytest.mark.parametrize("c,k,stride,pad,h", [(64, 3, 1, 1, 8), (128, 3, 2, 1, 8), (64, 1, 2, 0, 8), (256, 3, 1, 1, 2)])
 def test_tma_im2col_probe_matches_explicit_im2col(F, c, k, stride, pad, h):
     from baton_b200.ops import load
@@ -211,8 +209,6 @@ def test_tma_im2col_probe_matches_explicit_im2col(F, c, k, stride, pad, h):
     assert torch.equal(col, ref)
 
 
-@pytest.mark.skipif(os.environ.get("BATON_CONV_IGEMM") != "1",
-                    reason="experimental implicit-GEMM convolution (TMA im2col operands): opt in with BATON_CONV_IGEMM=1")
 @pytest.mark.parametrize("cin,cout,k,stride,pad,h,n", [(64, 64, 3, 1, 1, 8, 128), (64, 128, 3, 2, 1, 8, 128),
                                                        (128, 128, 3, 1, 1, 4, 128), (256, 256, 3, 1, 1, 2, 128),
                                                        (64, 128, 1, 2, 0, 8, 128), (64, 64, 3, 1, 1, 5, 7)])
