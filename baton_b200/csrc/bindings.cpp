@@ -476,6 +476,21 @@ bool bn_bwd_fused(const at::Tensor& x, const at::Tensor& y, const at::Tensor& dy
   check(rc, "bn_bwd_fused");
   return true;
 }
+// single-kernel BatchNorm backward (cluster per channel slice); dy = dy_a (+ dy_b).  False: shape not supported.
+bool bn_bwd_cluster(const at::Tensor& x, const at::Tensor& y, const at::Tensor& dy_a, const std::optional<at::Tensor>& dy_b,
+                    at::Tensor dx, const std::optional<at::Tensor>& dres, const std::optional<at::Tensor>& gamma,
+                    const at::Tensor& mean, const at::Tensor& rstd, const std::optional<at::Tensor>& dgamma,
+                    const std::optional<at::Tensor>& dbeta, int64_t rows, int64_t C, bool relu, int64_t max_cluster) {
+  CHECK_CUDA(x);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rc = b200_bn_bwd_cluster(x.data_ptr(), y.data_ptr(), dy_a.data_ptr(), opt_ptr<const void>(dy_b), dx.data_ptr(),
+                                     opt_ptr<void>(dres), opt_ptr<const float>(gamma), mean.data_ptr<float>(),
+                                     rstd.data_ptr<float>(), opt_ptr<float>(dgamma), opt_ptr<float>(dbeta), rows, C, relu,
+                                     static_cast<int>(max_cluster), cur_stream());
+  if (rc == -2) return false;
+  check(rc, "bn_bwd_cluster");
+  return true;
+}
 void layernorm_fwd(const at::Tensor& x, const std::optional<at::Tensor>& res, at::Tensor y, const at::Tensor& gamma,
                    const at::Tensor& beta, at::Tensor mean, at::Tensor rstd, int64_t rows, int64_t C, double eps) {
   CHECK_CUDA(x);
@@ -542,6 +557,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attention_fwd", &attention_fwd);
   m.def("attention_bwd", &attention_bwd);
   m.def("bn_bwd_fused", &bn_bwd_fused);
+  m.def("bn_bwd_cluster", &bn_bwd_cluster);
   m.def("im2col_tma_probe", &im2col_tma_probe);
   m.def("conv_igemm_fwd", &conv_igemm_fwd);
   m.def("conv_igemm_wgrad", &conv_igemm_wgrad);

@@ -913,7 +913,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* cstat = reinterpret_cast<float*>(tmem_slot + 4);   // [2 * BN] column statistics of this CTA's rows
+  float* cstat = reinterpret_cast<float*>(tmem_slot + 4);   // [4 warps][2 * BN] column statistics of this CTA's rows
 
   griddep_launch_dependents();  // PDL: the next kernel may start its prologue now
   const int warp = threadIdx.x >> 5;
@@ -1080,10 +1080,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const size_t elt = p.out_fp32 ? 4 : 2;
       const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * elt) % 16 == 0);
       const bool want_stats = p.col_stats != nullptr;
-      if (want_stats) {
-        for (int i = t; i < 2 * BN; i += 128) cstat[i] = 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
-      }
       // 128 % CG == 0: a thread always lands on the same 8 columns, so its statistics stay in registers
       float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int item = t; item < rows_per * CG; item += 128) {
@@ -1108,20 +1104,34 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (row < p.M && col0 < p.N) store_row_chunk<8>(p, row, col0, v, vec_ok);
       }
       if (want_stats) {
-        if (t < rows_per * CG) {
-          const int c = (t % CG) * 8;
+        // threads t, t + CG, t + 2 CG ... own the same 8 columns: fold the lanes of a warp with shuffles, park one
+        // row of partials per warp in shared memory (plain stores), then one thread per column adds the four warps
+        // and issues the global atomics.  (The previous shared-memory atomicAdd version serialised 16-way on a
+        // CAS loop: +8 us per launch in the captured step, profiles/r2_mb_layers.txt.)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            atomicAdd(cstat + c + j, cs[j]);
-            atomicAdd(cstat + BN + c + j, cq[j]);
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int o = CG; o < 32; o <<= 1) {
+            cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], o);
+            cq[j] += __shfl_xor_sync(0xffffffffu, cq[j], o);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = t; i < BN; i += 128)
-          if (n0 + i < p.N) {
-            atomicAdd(p.col_stats + n0 + i, cstat[i]);
-            atomicAdd(p.col_stats + p.N + n0 + i, cstat[BN + i]);
+        const int wq = t >> 5, ln = t & 31;
+        if (ln < CG) {                               // CG <= 32: lanes 0..CG-1 hold the warp's sums of columns ln*8..+7
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            cstat[wq * 2 * BN + ln * 8 + j] = cs[j];
+            cstat[wq * 2 * BN + BN + ln * 8 + j] = cq[j];
           }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        for (int i = t; i < 2 * BN; i += 128) {
+          const int col = i < BN ? i : i - BN;
+          if (n0 + col < p.N) {
+            const float v = cstat[i] + cstat[2 * BN + i] + cstat[4 * BN + i] + cstat[6 * BN + i];
+            atomicAdd(p.col_stats + (i < BN ? 0 : p.N) + n0 + col, v);
+          }
+        }
       }
     }
     cluster_sync_all();  // nobody leaves (and frees its smem) while a peer may still read it
@@ -1257,7 +1267,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
                       cudaStream_t stream) {
   using L = SmemLayout<BN>;
   constexpr int max_stages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  constexpr int max_smem = max_stages * L::STAGE_BYTES + (2 * MAX_STAGES + 1) * 8 + 16 + 2 * BN * 4 + 1024;
+  constexpr int max_smem = max_stages * L::STAGE_BYTES + (2 * MAX_STAGES + 1) * 8 + 16 + 8 * BN * 4 + 1024;
   static bool configured = false;
   if (!configured) {
     const int cap = max_smem > L::PART_BYTES + 4096 ? max_smem : L::PART_BYTES + 4096;
@@ -1270,7 +1280,7 @@ static int launch_cfg(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPa
   }
   int ring = p.stages * L::STAGE_BYTES;
   if (p.cluster_k > 1 && L::PART_BYTES > ring) ring = L::PART_BYTES;
-  int smem = ring + (2 * MAX_STAGES + 1) * 8 + 16 + 2 * BN * 4 + 1024;
+  int smem = ring + (2 * MAX_STAGES + 1) * 8 + 16 + 8 * BN * 4 + 1024;
   // occupancy cap: CTAs of this kernel per SM (shared memory is the limiter we control)
   static int max_ctas = -1;
   if (max_ctas < 0) {

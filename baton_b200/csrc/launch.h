@@ -127,6 +127,9 @@ int b200_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float
 int b200_bn_bwd_apply(const void* x, const void* y, const void* dy, void* dx, void* dres, const float* gamma,
                       const float* save_mean, const float* save_rstd, float* sums, float* dgamma, float* dbeta,
                       long long rows, int C, int relu, cudaStream_t stream);
+int b200_bn_bwd_cluster(const void* x, const void* y, const void* dy_a, const void* dy_b, void* dx, void* dres,
+                        const float* gamma, const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta,
+                        long long rows, int C, int relu, int max_cluster, cudaStream_t stream);
 int b200_bn_bwd_fused(const void* x, const void* y, const void* dy, void* dx, void* dres, const float* gamma,
                       const float* save_mean, const float* save_rstd, float* sums, float* dgamma, float* dbeta,
                       long long rows, int C, int relu, unsigned int* barrier, cudaStream_t stream);

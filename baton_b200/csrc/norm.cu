@@ -8,6 +8,31 @@
 
 namespace b200 {
 
+// cluster helpers (BatchNorm backward cluster kernel)
+__device__ __forceinline__ uint32_t cluster_ctarank_any() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank_y() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive_norm() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_norm() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all_norm() {
+  cluster_arrive_norm();
+  cluster_wait_norm();
+}
+__device__ __forceinline__ float ld_dsmem_f1(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------ BatchNorm statistics
 // sums[0:C] += sum_r x[r,c] ; sums[C:2C] += sum_r x[r,c]^2.  Block = 32 channel pairs x 8 row lanes.
 __global__ void __launch_bounds__(256)
@@ -878,6 +903,148 @@ bn_bwd_fused_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, co
   }
 }
 
+// ---- BatchNorm backward in ONE kernel, cluster edition (default path) ------------------------------------------
+// A thread-block CLUSTER owns a 16-channel slice of the [rows, C] activation (32 B = one sector per row and tensor)
+// and splits the rows between its CTAs.  Every thread reads its (x, y, dy) pieces ONCE and keeps them in
+// registers; the per-channel sums (sum dy', sum dy' * xhat) are reduced warp -> CTA (shared memory) -> cluster
+// (distributed shared memory, fixed order: deterministic), and after one cluster barrier the same registers produce
+// dx (and dres = dy').  No device-wide barrier (the channel slices are independent), no second pass over global
+// memory, no workspace: the two-kernel reduce + apply pair (3.1 + 4.7 us in the captured ResNet-18 step, in-graph
+// timeline profiles/r2_trace_resnet18_*.txt) becomes one launch.
+// The gradient may arrive in TWO pieces (dy = dy_a + dy_b): a ResNet block input receives the main-branch dgrad and
+// the residual-branch gradient, and summing them here removes the separate add kernel.
+constexpr int BNC_CW = 16;        // channels per cluster
+constexpr int BNC_LANES = 128;    // row lanes per CTA (256 threads = 128 rows x 2 sixteen-byte chunks)
+
+template <int ITER>
+__global__ void __launch_bounds__(256)
+bn_bwd_cluster_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy_a,
+                      const uint4* __restrict__ dy_b, uint4* __restrict__ dx, uint4* __restrict__ dres,
+                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C, int relu, int rows_per_cta) {
+  griddep_launch_dependents();
+  __shared__ float wpart[8][2][16];          // per-warp partials: [warp][chunk][8 x {sum_g, sum_gx}]
+  __shared__ __align__(16) float cpart[32];  // this CTA's partial: [0:16) sum_g, [16:32) sum_gx per channel of the slice
+  __shared__ float tot[32];
+  const int chunk = threadIdx.x & 1, lane_r = threadIdx.x >> 1;
+  const int c0 = blockIdx.x * BNC_CW + chunk * 8;            // first of this thread's 8 channels
+  const int C8 = C >> 3;
+  const uint32_t S = cluster_nctarank_y();
+  const uint32_t me = cluster_ctarank_any();
+  const int r_begin = static_cast<int>(me) * rows_per_cta;
+  int r_end = r_begin + rows_per_cta;
+  if (r_end > rows) r_end = rows;
+  float m[8], rs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { m[j] = mean[c0 + j]; rs[j] = rstd[c0 + j]; }    // written two kernels ago at the latest
+  griddep_wait();
+  float xh[ITER][8], g[ITER][8];
+  float sg[8], sgx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sgx[j] = 0.f; }
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int r = r_begin + it * BNC_LANES + lane_r;
+    if (r < r_end) {
+      const long long i = static_cast<long long>(r) * C8 + (c0 >> 3);
+      float xf[8];
+      unpack8_bn(x[i], xf);
+      unpack8_bn(dy_a[i], g[it]);
+      if (dy_b != nullptr) {
+        float t[8];
+        unpack8_bn(dy_b[i], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[it][j] += t[j];
+      }
+      if (relu) {
+        float yf[8];
+        unpack8_bn(y[i], yf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (!(yf[j] > 0.f)) g[it][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[it][j] = (xf[j] - m[j]) * rs[j];
+        sg[j] += g[it][j];
+        sgx[j] = fmaf(g[it][j], xh[it][j], sgx[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { xh[it][j] = 0.f; g[it][j] = 0.f; }
+    }
+  }
+  // warp reduce over the 16 row lanes that share this chunk (lane bit 0 = chunk)
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o = 2; o < 32; o <<= 1) {
+      sg[j] += __shfl_xor_sync(0xffffffffu, sg[j], o);
+      sgx[j] += __shfl_xor_sync(0xffffffffu, sgx[j], o);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wpart[warp][lane][j] = sg[j];
+      wpart[warp][lane][8 + j] = sgx[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {      // thread t: chunk = (t >> 3) & 1, j = t & 7, kind = t >> 4
+    const int kind = threadIdx.x >> 4, ch = (threadIdx.x >> 3) & 1, j = threadIdx.x & 7;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += wpart[w][ch][kind * 8 + j];
+    cpart[kind * 16 + ch * 8 + j] = t;
+  }
+  if (S > 1) {
+    cluster_sync_all_norm();
+  } else {
+    __syncthreads();
+  }
+  if (threadIdx.x < 32) {
+    float t = 0.f;
+    const uint32_t laddr = smem_u32(&cpart[threadIdx.x]);
+    for (uint32_t r = 0; r < S; ++r) t += (S > 1) ? ld_dsmem_f1(laddr, r) : cpart[threadIdx.x];
+    tot[threadIdx.x] = t;
+    if (me == 0) {             // one CTA per slice owns the parameter gradients of its 16 channels
+      const int c = blockIdx.x * BNC_CW + (threadIdx.x & 15);
+      if (threadIdx.x < 16) {
+        if (dbeta != nullptr) dbeta[c] += t;
+      } else if (dgamma != nullptr) {
+        dgamma[c] += t;
+      }
+    }
+  }
+  __syncthreads();
+  if (S > 1) cluster_arrive_norm();          // peers may exit once everybody has read everybody's partials
+  const float inv_rows = 1.f / static_cast<float>(rows);
+  float ka[8], kb[8], kc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ka[j] = (gamma != nullptr ? gamma[c0 + j] : 1.f) * rs[j];
+    kb[j] = tot[chunk * 8 + j] * inv_rows;
+    kc[j] = tot[16 + chunk * 8 + j] * inv_rows;
+  }
+#pragma unroll
+  for (int it = 0; it < ITER; ++it) {
+    const int r = r_begin + it * BNC_LANES + lane_r;
+    if (r < r_end) {
+      const long long i = static_cast<long long>(r) * C8 + (c0 >> 3);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = ka[j] * (g[it][j] - kb[j] - xh[it][j] * kc[j]);
+      dx[i] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      if (dres != nullptr)
+        dres[i] = make_uint4(pack_bf16x2(g[it][0], g[it][1]), pack_bf16x2(g[it][2], g[it][3]),
+                             pack_bf16x2(g[it][4], g[it][5]), pack_bf16x2(g[it][6], g[it][7]));
+    }
+  }
+  if (S > 1) cluster_wait_norm();
+}
+
 static inline bool colred_vec_ok(int C, const void* p0, const void* p1, const void* p2) {
   const int tpr = C >> 3;
   return C % 8 == 0 && tpr >= 1 && tpr <= 256 && (tpr & (tpr - 1)) == 0 &&
@@ -965,6 +1132,74 @@ extern "C" int b200_bn_bwd_apply(const void* x, const void* y, const void* dy, v
 }
 // EXPERIMENTAL single-kernel BatchNorm backward; returns -2 when the shape does not fit the vector layout or the
 // tensor is too large to stay L2-resident between the two phases (the caller then uses the two-kernel path).
+template <int ITER>
+static int launch_bn_bwd_cluster(dim3 grid, int S, cudaStream_t stream, const uint4* x, const uint4* y, const uint4* dy_a,
+                                 const uint4* dy_b, uint4* dx, uint4* dres, const float* gamma, const float* mean,
+                                 const float* rstd, float* dgamma, float* dbeta, int rows, int C, int relu, int rpc) {
+  static int np16 = -1;      // may clusters of 16 CTAs be used?  (non-portable size: opt-in per function)
+  if (np16 < 0) {
+    np16 = cudaFuncSetAttribute(bn_bwd_cluster_kernel<ITER>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    cudaGetLastError();
+  }
+  if (S > 8 && !np16) return -2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (S > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = static_cast<unsigned>(S);
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, bn_bwd_cluster_kernel<ITER>, x, y, dy_a, dy_b, dx, dres, gamma, mean, rstd, dgamma,
+                                     dbeta, rows, C, relu, rpc);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return static_cast<int>(cudaGetLastError());
+}
+
+// Single-kernel BatchNorm backward (cluster per 16-channel slice).  dy = dy_a (+ dy_b); dgamma / dbeta are
+// ACCUMULATED.  Returns -2 when the shape does not fit (C % 16, more than 16 x 1024 rows): use reduce + apply.
+extern "C" int b200_bn_bwd_cluster(const void* x, const void* y, const void* dy_a, const void* dy_b, void* dx, void* dres,
+                                   const float* gamma, const float* save_mean, const float* save_rstd, float* dgamma,
+                                   float* dbeta, long long rows, int C, int relu, int max_cluster, cudaStream_t stream) {
+  if (rows <= 0) return 0;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(relu ? y : x) |
+                       reinterpret_cast<uintptr_t>(dy_a) | reinterpret_cast<uintptr_t>(dy_b) |
+                       reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dres);
+  if (C % BNC_CW != 0 || (al & 15) || rows > (1ll << 30)) return -2;
+  if (max_cluster <= 0 || max_cluster > 16) max_cluster = 16;
+  const int slices = C / BNC_CW;
+  int S = 1;
+  while (S < max_cluster && (rows + S - 1) / S > BNC_LANES) S <<= 1;             // aim at one row per thread ...
+  while (S > 1 && static_cast<long long>(slices) * S > 2 * 148) S >>= 1;          // ... within two CTAs per SM
+  const int rpc = static_cast<int>((rows + S - 1) / S);
+  const int iters = (rpc + BNC_LANES - 1) / BNC_LANES;
+  if (iters > 8) return -2;
+  const dim3 grid(static_cast<unsigned>(slices), static_cast<unsigned>(S));
+#define BNC_GO(I)                                                                                                        \
+  return launch_bn_bwd_cluster<I>(grid, S, stream, reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(y), \
+                                  reinterpret_cast<const uint4*>(dy_a), reinterpret_cast<const uint4*>(dy_b),            \
+                                  reinterpret_cast<uint4*>(dx), reinterpret_cast<uint4*>(dres), gamma, save_mean,        \
+                                  save_rstd, dgamma, dbeta, static_cast<int>(rows), C, relu, rpc)
+  if (iters <= 1) BNC_GO(1);
+  if (iters <= 2) BNC_GO(2);
+  if (iters <= 4) BNC_GO(4);
+  BNC_GO(8);
+#undef BNC_GO
+}
+
 extern "C" int b200_bn_bwd_fused(const void* x, const void* y, const void* dy, void* dx, void* dres, const float* gamma,
                                  const float* save_mean, const float* save_rstd, float* sums, float* dgamma,
                                  float* dbeta, long long rows, int C, int relu, unsigned int* barrier,

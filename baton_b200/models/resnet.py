@@ -23,6 +23,33 @@ from ..ops import nn as bnn
 from .base import FederatedModule
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Hand-scheduled training step (no autograd engine).  The layer kernels are the ones the autograd Functions in
+# ``ops/nn.py`` call -- their ``forward`` / ``backward`` bodies are driven directly through ``bnn.Ctx`` -- but the
+# schedule is ours: the gradient of a block input travels as TWO pieces (main-branch dgrad, residual-branch
+# gradient) that the consuming BatchNorm-backward kernel sums while loading, so the eight element-wise adds autograd
+# would launch per step disappear; the downsample branch runs as a parallel branch of the captured graph.
+# ---------------------------------------------------------------------------------------------------------------
+def _conv_bn_fwd(conv: "bnn.Conv2d", bn: "bnn.BatchNorm2d", x, residual=None):
+    cc, cb = bnn.Ctx(), bnn.Ctx()
+    stats = conv._fusable_stats(x)
+    z = bnn._ConvFn.forward(cc, x, conv.weight, conv._w_bf16(), conv.kernel_size, conv.kernel_size, conv.stride,
+                            conv.padding, None, stats)
+    y = bnn._BNFn.forward(cb, z, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                          bn.eps, bn.momentum, bn.relu, True, bn.workspace, None, stats is not None)
+    return y, (cc, cb)
+
+
+def _conv_bn_bwd(ctxs, dy_a, dy_b=None, needs_dx=True):
+    """-> (gradient w.r.t. the conv input, gradient w.r.t. the residual input or None)"""
+    cc, cb = ctxs
+    cc.needs_dx = needs_dx
+    out = bnn._BNFn.backward(cb, dy_a, dy_b)
+    dz, dres = out[0], out[1]
+    dx = bnn._ConvFn.backward(cc, dz)[0]
+    return dx, dres
+
+
 class BasicBlock(nn.Module):
     expansion = 1
 
@@ -38,6 +65,8 @@ class BasicBlock(nn.Module):
         identity = x if self.downsample is None else self.downsample(x)
         out = self.bn1(self.conv1(x))
         return self.bn2(self.conv2(out), identity)
+
+    units = (("conv1", "bn1"), ("conv2", "bn2"))
 
 
 class Bottleneck(nn.Module):
@@ -58,6 +87,8 @@ class Bottleneck(nn.Module):
         out = self.bn1(self.conv1(x))
         out = self.bn2(self.conv2(out))
         return self.bn3(self.conv3(out), identity)
+
+    units = (("conv1", "bn1"), ("conv2", "bn2"), ("conv3", "bn3"))
 
 
 class _Downsample(nn.Sequential):
@@ -122,6 +153,77 @@ class ResNet(FederatedModule):
         x = self.maxpool(self.bn1(self.conv1(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(self.avgpool(x))
+
+    # ------------------------------------------------------------------ hand-scheduled step
+    def _block_fwd(self, blk, x, tape):
+        ds_ctx = None
+        identity = x
+        if blk.downsample is not None:
+            with bnn.BRANCH.fork(x):                      # parallel graph branch: 1x1 conv + BN of the shortcut
+                identity, ds_ctx = _conv_bn_fwd(blk.downsample[0], blk.downsample[1], x)
+        out = x
+        ctxs = []
+        n = len(blk.units)
+        for i, (cn, bnn_) in enumerate(blk.units):
+            last = i == n - 1
+            if last:
+                bnn.BRANCH.join()                         # the shortcut must have landed before the residual add
+            out, c = _conv_bn_fwd(getattr(blk, cn), getattr(blk, bnn_), out, identity if last else None)
+            ctxs.append(c)
+        tape.append((ctxs, ds_ctx))
+        return out
+
+    def _block_bwd(self, entry, pieces):
+        """``pieces``: 1-2 tensors whose sum is the gradient of the block output -> pieces of the block-input gradient"""
+        ctxs, ds_ctx = entry
+        d, dres = _conv_bn_bwd(ctxs[-1], pieces[0], pieces[1] if len(pieces) > 1 else None)
+        dx_ds = None
+        if ds_ctx is not None:
+            with bnn.BRANCH.fork(dres):                   # shortcut backward in parallel with the main branch
+                dx_ds, _ = _conv_bn_bwd(ds_ctx, dres)
+        for c in reversed(ctxs[:-1]):
+            d, _ = _conv_bn_bwd(c, d)
+        if ds_ctx is not None:
+            bnn.BRANCH.join()
+            return [d, dx_ds]
+        return [d, dres]
+
+    def explicit_step(self, x, target, loss_acc=None):
+        """Forward + loss + backward of one batch with parameter gradients accumulated into the arena (the same
+        contract as ``loss.backward()`` on ``forward``); returns the device ``[mean loss, #correct]`` pair.
+        CUDA + arena-adopted training mode only."""
+        F = bnn.F
+        if self.stats_workspace is not None:
+            self.stats_workspace.zero_()
+        h, stem = _conv_bn_fwd(self.conv1, self.bn1, x)
+        cp = bnn.Ctx()
+        h = bnn._MaxPoolFn.forward(cp, h, self.maxpool.k, self.maxpool.stride, self.maxpool.pad)
+        tape = []
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                h = self._block_fwd(blk, h, tape)
+        ca = None
+        if h.shape[1] == 1 and h.shape[2] == 1:
+            feat = h.reshape(h.shape[0], h.shape[3])
+        else:
+            ca = bnn.Ctx()
+            feat = bnn._AvgPoolFn.forward(ca, h)
+        cl = bnn.Ctx()
+        fc = self.fc
+        logits = bnn._LinearFn.forward(cl, feat, fc.weight, fc.bias, bnn._shadow(fc, "weight", fc.weight), fc.act,
+                                       fc.out_fp32, None, None)
+        cl.needs_dx = True
+        stats, dlogits = F.softmax_xent(logits.contiguous(), target, want_grad=True, acc=loss_acc)
+        d = bnn._LinearFn.backward(cl, dlogits)[0]
+        d = d.reshape(h.shape) if ca is None else bnn._AvgPoolFn.backward(ca, d)
+        pieces = [d]
+        for entry in reversed(tape):
+            pieces = self._block_bwd(entry, pieces)
+        d = pieces[0] if len(pieces) == 1 else F.add(pieces[0], pieces[1])
+        d = bnn._MaxPoolFn.backward(cp, d)[0]
+        _conv_bn_bwd(stem, d, needs_dx=False)
+        bnn.WGRAD.join()
+        return stats
 
     # ------------------------------------------------------------------
     def build_workspace(self, device) -> torch.Tensor:

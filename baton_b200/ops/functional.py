@@ -304,11 +304,13 @@ def avgpool_bwd(dy: torch.Tensor, in_shape) -> torch.Tensor:
 
 # ---------------------------------------------------------------------------- losses
 def softmax_xent(logits: torch.Tensor, target: torch.Tensor, want_grad: bool = True,
-                 grad_dtype: Optional[torch.dtype] = None):
+                 grad_dtype: Optional[torch.dtype] = None, acc: Optional[torch.Tensor] = None):
     """Fused softmax cross-entropy: returns ``(acc, dlogits)`` where ``acc[0]`` is the
-    batch-mean loss and ``acc[1]`` the number of correct predictions."""
+    batch-mean loss and ``acc[1]`` the number of correct predictions.  ``acc`` (fp32 ``[2]``) may be supplied: the
+    kernel ADDS into it (a device-side running sum over the steps of an epoch, no extra kernels)."""
     rows, c = logits.shape
-    acc = torch.zeros(2, dtype=torch.float32, device=logits.device)
+    if acc is None:
+        acc = torch.zeros(2, dtype=torch.float32, device=logits.device)
     dl = torch.empty_like(logits, dtype=grad_dtype or logits.dtype) if want_grad else None
     load().softmax_xent(logits, target, dl, acc, rows, c, logits.stride(0), 1.0 / rows)
     return acc, dl

@@ -59,6 +59,21 @@ def _anchor(x, *params):
     return None
 
 
+class Ctx:
+    """Stand-in for the autograd context: lets a hand-scheduled training step (``models/resnet.py``
+    ``ResNet.explicit_step``) call the ``forward`` / ``backward`` bodies of the Functions below directly, in its own
+    order and with its own fusions (two-piece gradients, parallel branches), without the autograd engine."""
+
+    def __init__(self):
+        self.saved_tensors = ()
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+    def mark_non_differentiable(self, *a):
+        pass
+
+
 class _WgradOverlap:
     """Weight-gradient GEMMs only feed the optimizer, so they are forked onto a side stream and overlap
     the dgrad -> BatchNorm-backward chain of the layers below (inside a captured graph this becomes a
@@ -110,6 +125,43 @@ class _WgradOverlap:
 
 
 WGRAD = _WgradOverlap()
+
+
+class _Branch:
+    """Fork / join of an independent sub-chain (the shortcut conv + BN of a ResNet block, forward and backward) onto a
+    side stream, so that inside a captured step it becomes a parallel graph branch.  These kernels use a fraction of
+    the SMs and are latency bound, so two chains side by side cost the time of the longer one."""
+
+    def __init__(self):
+        import os
+        self.enabled = os.environ.get("BATON_BRANCH_OVERLAP", "1") != "0"
+        self.streams = {}
+        self.keep = []
+        self.pending = False
+
+    def fork(self, *keep):
+        import contextlib
+        if not self.enabled or not keep[0].is_cuda:
+            return contextlib.nullcontext()
+        dev = keep[0].device
+        side = self.streams.get(dev)
+        if side is None:
+            side = self.streams[dev] = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        self.keep.append(keep)
+        self.pending = True
+        return torch.cuda.stream(side)
+
+    def join(self):
+        if not self.pending:
+            return
+        for dev, side in self.streams.items():
+            torch.cuda.current_stream(dev).wait_stream(side)
+        self.keep.clear()
+        self.pending = False
+
+
+BRANCH = _Branch()
 
 
 def _grad_target(p: Optional[torch.Tensor]):
@@ -380,7 +432,10 @@ class Conv2d(nn.Module):
 
 
 # ================================================================================ BatchNorm (+residual +ReLU)
-_BN_BWD_FUSED = __import__("os").environ.get("BATON_BN_BWD_FUSED", "0") == "1"   # opt-in until validated on hardware
+_BN_BWD_FUSED = __import__("os").environ.get("BATON_BN_BWD_FUSED", "0") == "1"   # grid-barrier variant: validated, slower
+# single-kernel BatchNorm backward, one thread-block cluster per 16-channel slice (csrc/norm.cu)
+_BN_BWD_CLUSTER = __import__("os").environ.get("BATON_BN_BWD_CLUSTER", "1") == "1"
+_BN_BWD_MAX_CLUSTER = int(__import__("os").environ.get("BATON_BN_BWD_MAX_CLUSTER", "16"))
 _GRID_BARRIERS = {}
 
 
@@ -416,7 +471,9 @@ class _BNFn(torch.autograd.Function):
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dy_b=None):
+        """``dy_b``: optional second piece of the incoming gradient (``dy + dy_b``), summed inside the kernel --
+        only the hand-scheduled step passes it (autograd sums gradients itself)."""
         C_ = load()
         x, y, mean, rstd = ctx.saved_tensors
         if not dy.is_contiguous():
@@ -431,7 +488,12 @@ class _BNFn(torch.autograd.Function):
         if tb is None:
             gb = tb = torch.zeros(ctx.c, dtype=torch.float32, device=x.device)
         done = False
-        if _BN_BWD_FUSED:       # experimental: reduce + device-wide barrier + apply in one kernel
+        if _BN_BWD_CLUSTER:
+            done = C_.bn_bwd_cluster(x, y, dy, dy_b, dx, dres, gamma, mean, rstd, tg, tb, ctx.rows, ctx.c, ctx.relu,
+                                     _BN_BWD_MAX_CLUSTER)
+        if not done and dy_b is not None:
+            dy = F.add(dy, dy_b.contiguous())
+        if not done and _BN_BWD_FUSED:       # reduce + device-wide barrier + apply in one kernel
             done = C_.bn_bwd_fused(x, y, dy, dx, dres, gamma, mean, rstd, ctx.sums_b, tg, tb, ctx.rows, ctx.c, ctx.relu,
                                    _grid_barrier_words(x.device))
         if not done:

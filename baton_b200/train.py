@@ -91,6 +91,8 @@ class GraphedLocalSGD:
         self.nesterov = nesterov
         self.use_graph = use_graph
         self.input_dtype = input_dtype
+        import os
+        self.explicit = os.environ.get("BATON_EXPLICIT_STEP", "1") != "0"   # models that offer a hand-scheduled step
         dev = arena.device
         self.device = dev
         self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)
@@ -115,15 +117,23 @@ class GraphedLocalSGD:
         ws = getattr(self.model, "stats_workspace", None)
         if ws is not None and not getattr(self.model, "zeroes_own_workspace", False):
             ws.zero_()
-        out = self.model(xb)
-        loss, stats = self._loss(out, yb)
-        loss.backward()
-        self.bnn.WGRAD.join()      # weight-gradient GEMMs run on a side stream; they must land before the step
+        explicit = getattr(self.model, "explicit_step", None) if self.explicit else None
+        if explicit is not None and self.loss_kind in ("ce", "cross_entropy"):
+            # hand-scheduled forward + loss + backward (no autograd engine): two-piece block gradients, parallel shortcut
+            # branch; the loss kernel accumulates straight into the epoch's running sums
+            explicit(xb, yb, loss_acc=self.loss_acc)
+            stats = None
+        else:
+            out = self.model(xb)
+            loss, stats = self._loss(out, yb)
+            loss.backward()
+            self.bnn.WGRAD.join()      # weight-gradient GEMMs run on a side stream; they must land before the step
         a = self.arena
         F.fused_sgd(a.theta[: a.n_param], a.grad, self.hyper, a.momentum,
                     a.theta_bf16[: a.n_param] if a.theta_bf16 is not None else None,
                     zero_grad=True, nesterov=self.nesterov)
-        self.loss_acc.add_(stats)
+        if stats is not None:
+            self.loss_acc.add_(stats)
 
     def _set_hyper(self, lr, momentum, weight_decay, dampening=0.0):
         vals = (float(lr), float(momentum), float(weight_decay), float(dampening))

@@ -430,6 +430,46 @@ def test_batchnorm_backward_single_kernel_matches_two_kernel_path(bnn, n, h, c):
         assert _rel(a, b) < 1e-2
 
 
+@pytest.mark.parametrize("n,h,c,relu,two", [(128, 8, 64, True, True), (128, 8, 64, False, False), (128, 4, 128, True, True),
+                                            (128, 2, 256, True, False), (128, 1, 512, True, True), (9, 5, 128, True, True),
+                                            (128, 16, 64, True, False), (32, 8, 256, True, True)])
+def test_batchnorm_backward_cluster_kernel_matches_two_kernel_path(bnn, n, h, c, relu, two):
+    """Single-kernel BatchNorm backward (one thread-block cluster per 16-channel slice, csrc/norm.cu) against the
+    reduce + apply pair, including the two-piece gradient (dy = dy_a + dy_b) and every register-cache depth."""
+    from baton_b200.ops import load
+    C_ = load()
+    torch.manual_seed(13)
+    dev = _dev()
+    rows = n * h * h
+    x = (torch.randn(rows, c, device=dev) * 2 + 0.5).to(BF16)
+    mean = x.float().mean(0)
+    rstd = (x.float().var(0, unbiased=False) + 1e-5).rsqrt()
+    gamma = torch.rand(c, device=dev) + 0.5
+    y = (torch.randn(rows, c, device=dev)).to(BF16)            # only its sign matters (ReLU mask)
+    dy_a = torch.randn(rows, c, device=dev).to(BF16)
+    dy_b = torch.randn(rows, c, device=dev).to(BF16) if two else None
+    dy = dy_a if dy_b is None else (dy_a.float() + dy_b.float())
+    # fp32 oracle
+    g = dy.float() * ((y.float() > 0).float() if relu else 1.0)
+    xh = (x.float() - mean) * rstd
+    dxr = gamma * rstd * (g - g.mean(0) - xh * (g * xh).mean(0))
+    dgr, dbr = (g * xh).sum(0), g.sum(0)
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x)
+    dg = torch.ones(c, device=dev)       # accumulate semantics: starts at 1
+    db = torch.ones(c, device=dev)
+    for cap in (16, 8, 2):
+        dg.fill_(1.0); db.fill_(1.0)
+        ok = C_.bn_bwd_cluster(x, y, dy_a, dy_b, dx, dres, gamma, mean, rstd, dg, db, rows, c, relu, cap)
+        torch.cuda.synchronize()
+        if not ok:
+            assert rows > cap * 1024
+            continue
+        assert _rel(dx, dxr) < 2e-2
+        assert _rel(dres, g) < 1e-2
+        assert _rel(dg - 1.0, dgr) < 1e-2 and _rel(db - 1.0, dbr) < 1e-2
+
+
 def test_layernorm_softmax(bnn):
     torch.manual_seed(8)
     dev = _dev()
