@@ -26,6 +26,7 @@ class GpuExperimentWorker(ExperimentWorker):
                  backend: str = "fused", group=None, loss: str = "ce", wire_dtype: str = "bf16",
                  momentum: float = 0.0, use_graph: bool = True, n_ctas: int = 64, **kwargs):
         self.device = torch.device(device)
+        torch.cuda.set_device(self.device)          # the constructing thread (usually the event-loop thread)
         self.arena = ParamArena(model, self.device, momentum=momentum > 0)
         if hasattr(model, "build_workspace"):
             model.build_workspace(self.device)

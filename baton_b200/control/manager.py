@@ -178,15 +178,28 @@ class Experiment:
             await self.pull_global()
         body = self.plane.round_start_message(self.model, update_name, n_epoch, extra)
         self._round_bytes += len(body) * len(chosen)
+        # seated planes: a seat that has never been given the global model (new, re-registered, or the manager resumed
+        # a checkpoint) gets the full state_dict with this round_start; everybody else gets metadata only
+        per_client = None
+        need_model = self.plane.unsynced(self, chosen) if hasattr(self.plane, "unsynced") else []
+        if need_model:
+            await self.pull_global()
+            full = self.plane.round_start_with_model(self.model, update_name, n_epoch, extra)
+            self._round_bytes += (len(full) - len(body)) * len(need_model)
+            need = set(need_model)
+            per_client = lambda c: {"data": full} if c in need else {}      # noqa: E731
         async def _accepted(client_id: str, ok: bool) -> None:
             # a participant joins the round the moment ITS notify returns: a fast client may finish training and
             # POST its update while slower peers are still receiving the round (reference manager.py:87-89 only
             # registered participants after the whole gather)
             if ok and self.update_manager.in_progress and self.update_manager.update_name == update_name:
                 self.update_manager.client_start(client_id)
+            if ok and client_id in self.client_manager.clients and hasattr(self.plane, "unsynced"):
+                self.client_manager.clients[client_id]["model_synced"] = True
 
         result = await self.client_manager.notify_clients(
-            "round_start", http_method="POST", data=body, clients=chosen, client_callback=_accepted)
+            "round_start", http_method="POST", data=body, clients=chosen, client_callback=_accepted,
+            per_client_kwargs=per_client)
         if not self.update_manager.in_progress or self.update_manager.update_name != update_name:
             return dict(result)          # every participant already reported and the round closed meanwhile
         if not self.update_manager:

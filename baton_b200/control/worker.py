@@ -83,7 +83,10 @@ class ExperimentWorker:
         self.last_loss_history: list = []
         self._session: Optional[aiohttp.ClientSession] = None
         self._heartbeat_manager: Optional[PeriodicTask] = None
-        self._executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix="baton-train")
+        # one training thread; a GPU-seated worker (``self.device`` set by the subclass before this constructor runs)
+        # binds it to its own CUDA device -- new threads start on device 0
+        self._executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix="baton-train",
+                                            initializer=self._bind_device)
         self._round_task: Optional[asyncio.Task] = None
         self._auto_register = auto_register
         # fault-injection seams used by the test-suite
@@ -162,6 +165,12 @@ class ExperimentWorker:
             await asyncio.sleep(timeout)
             timeout = min(timeout * 2, MAX_BACKOFF)
 
+    def _bind_device(self) -> None:
+        dev = getattr(self, "device", None)
+        if dev is not None and getattr(dev, "type", None) == "cuda":
+            import torch
+            torch.cuda.set_device(dev)
+
     # -- routes ---------------------------------------------------------------
     def register_handlers(self) -> None:
         r = self.app.router
@@ -221,10 +230,15 @@ class ExperimentWorker:
         if self.fail_next_rounds > 0:
             self.fail_next_rounds -= 1
             raise RuntimeError("injected training failure")
+        import time
+        t0 = time.perf_counter()
         data, n_samples = self.get_data()
         train = resolve_train_fn(self.model)
         loss_history = train(*data, n_epoch=n_epoch, **self.train_kwargs)
-        return n_samples, [float(x) for x in loss_history]
+        out = n_samples, [float(x) for x in loss_history]     # reading the losses waits for the device
+        if getattr(self, "train_seconds", None) is not None:
+            self.train_seconds.append(time.perf_counter() - t0)
+        return out
 
     async def _run_round(self, update_name: str, n_epoch: int) -> None:
         try:

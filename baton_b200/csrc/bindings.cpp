@@ -210,13 +210,13 @@ void dequant_mx(const at::Tensor& q, const at::Tensor& sf, at::Tensor out, int64
 }
 
 void fused_sgd(at::Tensor w, at::Tensor g, const std::optional<at::Tensor>& mom, const std::optional<at::Tensor>& wb,
-               const at::Tensor& hyper, bool zero_grad, bool nesterov) {
+               const at::Tensor& hyper, bool zero_grad, bool nesterov, int64_t max_ctas) {
   CHECK_CUDA(w);
   TORCH_CHECK(w.scalar_type() == at::kFloat && g.scalar_type() == at::kFloat && hyper.scalar_type() == at::kFloat);
   TORCH_CHECK(w.is_contiguous() && g.is_contiguous() && w.numel() == g.numel());
   const c10::cuda::CUDAGuard guard(w.device());
   check(b200_fused_sgd(w.data_ptr<float>(), g.data_ptr<float>(), opt_ptr<float>(mom), opt_ptr<void>(wb), w.numel(),
-                       hyper.data_ptr<float>(), zero_grad, nesterov, cur_stream()),
+                       hyper.data_ptr<float>(), zero_grad, nesterov, static_cast<int>(max_ctas), cur_stream()),
         "fused_sgd");
 }
 
@@ -397,16 +397,18 @@ void maxpool(const at::Tensor& x, at::Tensor y, at::Tensor arg, int64_t N, int64
              int64_t stride, int64_t pad, int64_t Ho, int64_t Wo) {
   CHECK_CUDA(x);
   const c10::cuda::CUDAGuard guard(x.device());
-  check(b200_maxpool_nhwc(x.data_ptr(), y.data_ptr(), arg.data_ptr<int>(), N, H, W, C, k, stride, pad, Ho, Wo,
-                          cur_stream()),
+  const int u8 = arg.scalar_type() == at::kByte;      // byte-sized winners: the 16-byte kernels
+  check(b200_maxpool_nhwc(x.data_ptr(), y.data_ptr(), reinterpret_cast<int*>(arg.data_ptr()), N, H, W, C, k, stride, pad,
+                          Ho, Wo, u8, cur_stream()),
         "maxpool");
 }
-void maxpool_bwd(const at::Tensor& dy, const at::Tensor& arg, at::Tensor dx, int64_t N, int64_t H, int64_t W, int64_t C,
-                 int64_t Ho, int64_t Wo, int64_t k, int64_t stride, int64_t pad) {
+void maxpool_bwd(const at::Tensor& dy, const std::optional<at::Tensor>& dy_b, const at::Tensor& arg, at::Tensor dx,
+                 int64_t N, int64_t H, int64_t W, int64_t C, int64_t Ho, int64_t Wo, int64_t k, int64_t stride, int64_t pad) {
   CHECK_CUDA(dy);
   const c10::cuda::CUDAGuard guard(dy.device());
-  check(b200_maxpool_bwd_nhwc(dy.data_ptr(), arg.data_ptr<int>(), dx.data_ptr(), N, H, W, C, Ho, Wo, k, stride, pad,
-                              cur_stream()),
+  const int u8 = arg.scalar_type() == at::kByte;
+  check(b200_maxpool_bwd_nhwc(dy.data_ptr(), opt_ptr<const void>(dy_b), reinterpret_cast<const int*>(arg.data_ptr()),
+                              dx.data_ptr(), N, H, W, C, Ho, Wo, k, stride, pad, u8, cur_stream()),
         "maxpool_bwd");
 }
 void avgpool(const at::Tensor& x, at::Tensor y, int64_t N, int64_t HW, int64_t C) {

@@ -201,6 +201,95 @@ maxpool_bwd_gather_kernel(const __nv_bfloat162* __restrict__ dy, const int2* __r
   }
 }
 
+// ---- 16-byte variants (C % 8 == 0): one thread = 8 channels of one pixel; the winner is remembered as ONE BYTE (the tap
+// index kh * k + kw inside the window) instead of a 4-byte flat position, and the backward optionally sums a two-piece
+// gradient (dy_a + dy_b) while loading.  The scalar kernels above moved 4 bytes per request and took 8.4 / 27.6 us for
+// the 32x32-input ResNet stem inside the captured step (in-graph timeline, profiles/).
+__global__ void __launch_bounds__(CV_THREADS)
+maxpool_vec_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ arg, int N, int H, int W, int C8,
+                   int k, int stride, int pad, int Ho, int Wo) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const long long total = static_cast<long long>(N) * Ho * Wo * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    long long t = i / C8;
+    const int wo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float m[8];
+    uint32_t a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { m[j] = -INFINITY; a[j] = 255u; }
+    for (int kh = 0; kh < k; ++kh) {
+      const int h = ho * stride - pad + kh;
+      if (h < 0 || h >= H) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int w = wo * stride - pad + kw;
+        if (w < 0 || w >= W) continue;
+        const uint4 v = x[((static_cast<long long>(n) * H + h) * W + w) * C8 + c8];
+        const float2 p0 = unpack_bf16x2(v.x), p1 = unpack_bf16x2(v.y), p2 = unpack_bf16x2(v.z), p3 = unpack_bf16x2(v.w);
+        const float f[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+        const uint32_t tap = static_cast<uint32_t>(kh * k + kw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > m[j]) { m[j] = f[j]; a[j] = tap; }
+      }
+    }
+    y[i] = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+    arg[i] = make_uint2(a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24), a[4] | (a[5] << 8) | (a[6] << 16) | (a[7] << 24));
+  }
+}
+
+__global__ void __launch_bounds__(CV_THREADS)
+maxpool_bwd_vec_kernel(const uint4* __restrict__ dy_a, const uint4* __restrict__ dy_b, const uint2* __restrict__ arg,
+                       uint4* __restrict__ dx, int N, int H, int W, int C8, int Ho, int Wo, int k, int stride, int pad) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const long long total = static_cast<long long>(N) * H * W * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    long long t = i / C8;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int kh = 0; kh < k; ++kh) {
+      const int hh = h + pad - kh;
+      if (hh < 0 || hh % stride) continue;
+      const int ho = hh / stride;
+      if (ho >= Ho) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int ww = w + pad - kw;
+        if (ww < 0 || ww % stride) continue;
+        const int wo = ww / stride;
+        if (wo >= Wo) continue;
+        const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C8 + c8;
+        const uint2 a = arg[o];
+        uint4 v = dy_a[o];
+        float2 p0 = unpack_bf16x2(v.x), p1 = unpack_bf16x2(v.y), p2 = unpack_bf16x2(v.z), p3 = unpack_bf16x2(v.w);
+        float f[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+        if (dy_b != nullptr) {
+          v = dy_b[o];
+          p0 = unpack_bf16x2(v.x); p1 = unpack_bf16x2(v.y); p2 = unpack_bf16x2(v.z); p3 = unpack_bf16x2(v.w);
+          f[0] += p0.x; f[1] += p0.y; f[2] += p1.x; f[3] += p1.y; f[4] += p2.x; f[5] += p2.y; f[6] += p3.x; f[7] += p3.y;
+        }
+        const uint32_t tap = static_cast<uint32_t>(kh * k + kw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+          if (aj == tap) g[j] += f[j];
+        }
+      }
+    }
+    dx[i] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
+  }
+}
+
 // global average pool [N, HW, C] -> [N, C] and its backward
 __global__ void __launch_bounds__(CV_THREADS)
 avgpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int HW, int C) {
@@ -262,8 +351,17 @@ extern "C" int b200_col2im_nhwc(const void* col, void* dx, int N, int H, int W, 
                                                                stride, pad, Ho, Wo, kp / 8);
   RET_LAST();
 }
+// argmax: int32 flat positions (scalar path) or, when arg_u8 != 0 (C % 8 == 0, k * k <= 255), one byte per element
 extern "C" int b200_maxpool_nhwc(const void* x, void* y, int* argmax, int N, int H, int W, int C, int k, int stride,
-                                 int pad, int Ho, int Wo, cudaStream_t stream) {
+                                 int pad, int Ho, int Wo, int arg_u8, cudaStream_t stream) {
+  if (arg_u8) {
+    if (C % 8 || k * k > 255) return -2;
+    const long long total8 = static_cast<long long>(N) * Ho * Wo * (C / 8);
+    if (total8 <= 0) return 0;
+    launch_pdl(maxpool_vec_kernel, cv_grid(total8), CV_THREADS, 0, stream, reinterpret_cast<const uint4*>(x),
+               reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(argmax), N, H, W, C / 8, k, stride, pad, Ho, Wo);
+    RET_LAST();
+  }
   if (C % 2) return -2;
   const long long total = static_cast<long long>(N) * Ho * Wo * (C / 2);
   if (total <= 0) return 0;
@@ -273,8 +371,18 @@ extern "C" int b200_maxpool_nhwc(const void* x, void* y, int* argmax, int N, int
                                                             pad, Ho, Wo);
   RET_LAST();
 }
-extern "C" int b200_maxpool_bwd_nhwc(const void* dy, const int* argmax, void* dx, int N, int H, int W, int C, int Ho,
-                                     int Wo, int k, int stride, int pad, cudaStream_t stream) {
+extern "C" int b200_maxpool_bwd_nhwc(const void* dy, const void* dy_b, const int* argmax, void* dx, int N, int H, int W,
+                                     int C, int Ho, int Wo, int k, int stride, int pad, int arg_u8, cudaStream_t stream) {
+  if (arg_u8) {
+    if (C % 8) return -2;
+    const long long total8 = static_cast<long long>(N) * H * W * (C / 8);
+    if (total8 <= 0) return 0;
+    launch_pdl(maxpool_bwd_vec_kernel, cv_grid(total8), CV_THREADS, 0, stream, reinterpret_cast<const uint4*>(dy),
+               reinterpret_cast<const uint4*>(dy_b), reinterpret_cast<const uint2*>(argmax), reinterpret_cast<uint4*>(dx), N,
+               H, W, C / 8, Ho, Wo, k, stride, pad);
+    RET_LAST();
+  }
+  if (dy_b != nullptr) return -2;
   if (C % 2) return -2;
   const long long total = static_cast<long long>(N) * H * W * (C / 2);
   if (total <= 0) return 0;

@@ -388,10 +388,12 @@ embedding_bwd_kernel(const uint4* __restrict__ dy, const long long* __restrict__
 using namespace b200;
 #define RET_LAST() return static_cast<int>(cudaGetLastError())
 
+// max_ctas > 0 caps the grid (grid-stride kernel): an optimizer slice that runs BESIDE latency-bound compute kernels on
+// another stream must leave SM slots free for them
 extern "C" int b200_fused_sgd(float* w, float* g, float* mom, void* w_bf16, long long n, const float* hyper,
-                              int zero_grad, int nesterov, cudaStream_t stream) {
+                              int zero_grad, int nesterov, int max_ctas, cudaStream_t stream) {
   if (n <= 0) return 0;
-  launch_pdl(fused_sgd_kernel, ew_grid(n >> 2), EW_THREADS, 0, stream, w, g, mom, reinterpret_cast<__nv_bfloat16*>(w_bf16), n,
+  launch_pdl(fused_sgd_kernel, max_ctas > 0 ? ew_grid(n >> 2, max_ctas) : ew_grid(n >> 2), EW_THREADS, 0, stream, w, g, mom, reinterpret_cast<__nv_bfloat16*>(w_bf16), n,
                                                                 hyper, zero_grad, nesterov);
   RET_LAST();
 }

@@ -1430,9 +1430,12 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
     if (bn == 256) return launch_persistent<256, 4>(ta, tb, p, num_tiles, stream);
     return launch_persistent<128, 6>(ta, tb, p, num_tiles, stream);
   }
+  // short K loops (stem convolution: 3 k tiles, 1x1 shortcuts: 1-4) do not need a deep ring: a shallow one asks for
+  // little shared memory, so two CTAs share an SM and a grid of > 148 tiles still runs as one wave
+  const bool shallow = per <= 4 && !p.batched;
   if (bn == 256) return launch_fixed<256, 4>(ta, tb, p, grid, stream);
-  if (bn == 128) return launch_fixed<128, 6>(ta, tb, p, grid, stream);
-  return launch_fixed<64, 8>(ta, tb, p, grid, stream);
+  if (bn == 128) return shallow ? launch_fixed<128, 3>(ta, tb, p, grid, stream) : launch_fixed<128, 6>(ta, tb, p, grid, stream);
+  return shallow ? launch_fixed<64, 4>(ta, tb, p, grid, stream) : launch_fixed<64, 8>(ta, tb, p, grid, stream);
 }
 
 // Strided-batched GEMM (attention): for z = outer * n_inner + inner
@@ -1538,9 +1541,10 @@ extern "C" int b200_conv_igemm_fwd(const void* x, const void* w, void* y, int N,
     if (bn == 128) return launch_cfg<128, 1>(ta, tb, p, grid, stream);
     return launch_cfg<64, 1>(ta, tb, p, grid, stream);
   }
+  const bool shallow = per <= 4;
   if (bn == 256) return launch_fixed<256, 4, 1>(ta, tb, p, grid, stream);
-  if (bn == 128) return launch_fixed<128, 6, 1>(ta, tb, p, grid, stream);
-  return launch_fixed<64, 8, 1>(ta, tb, p, grid, stream);
+  if (bn == 128) return shallow ? launch_fixed<128, 3, 1>(ta, tb, p, grid, stream) : launch_fixed<128, 6, 1>(ta, tb, p, grid, stream);
+  return shallow ? launch_fixed<64, 4, 1>(ta, tb, p, grid, stream) : launch_fixed<64, 8, 1>(ta, tb, p, grid, stream);
 }
 
 // input gradient of a STRIDE-1 convolution: dx[N*H*W, Cin] = im2col_{pad' = K-1-pad}(dy) * flip(w), dy NHWC bf16

@@ -49,7 +49,7 @@ int b200_gemm_simt(const void* a, const void* b, void* d, const float* bias, int
 // ---- elementwise.cu
 // hyper = device float[4] {lr, momentum, weight_decay, dampening}
 int b200_fused_sgd(float* w, float* g, float* mom, void* w_bf16, long long n, const float* hyper, int zero_grad,
-                   int nesterov, cudaStream_t stream);
+                   int nesterov, int max_ctas, cudaStream_t stream);
 int b200_weighted_sum(void* dst, const void* const* srcs, const float* weights, int n_src, long long n, int dtype,
                       cudaStream_t stream);  // dtype: 0 fp32, 1 bf16
 int b200_cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
@@ -111,9 +111,9 @@ int b200_im2col_nhwc(const void* x, void* col, int N, int H, int W, int C, int K
 int b200_col2im_nhwc(const void* col, void* dx, int N, int H, int W, int C, int KH, int KW, int stride, int pad,
                      int Ho, int Wo, int kp, cudaStream_t stream);
 int b200_maxpool_nhwc(const void* x, void* y, int* argmax, int N, int H, int W, int C, int k, int stride, int pad,
-                      int Ho, int Wo, cudaStream_t stream);
-int b200_maxpool_bwd_nhwc(const void* dy, const int* argmax, void* dx, int N, int H, int W, int C, int Ho, int Wo,
-                          int k, int stride, int pad, cudaStream_t stream);
+                      int Ho, int Wo, int arg_u8, cudaStream_t stream);
+int b200_maxpool_bwd_nhwc(const void* dy, const void* dy_b, const int* argmax, void* dx, int N, int H, int W, int C, int Ho,
+                          int Wo, int k, int stride, int pad, int arg_u8, cudaStream_t stream);
 int b200_avgpool_nhwc(const void* x, void* y, int N, int HW, int C, cudaStream_t stream);
 int b200_avgpool_bwd_nhwc(const void* dy, void* dx, int N, int HW, int C, cudaStream_t stream);
 

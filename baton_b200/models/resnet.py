@@ -188,10 +188,17 @@ class ResNet(FederatedModule):
             return [d, dx_ds]
         return [d, dres]
 
-    def explicit_step(self, x, target, loss_acc=None):
+    tail_split_prefix = "layer3."       # parameters from here on (layer3, layer4, fc) receive their gradients FIRST
+
+    def explicit_step(self, x, target, loss_acc=None, hooks=None):
         """Forward + loss + backward of one batch with parameter gradients accumulated into the arena (the same
         contract as ``loss.backward()`` on ``forward``); returns the device ``[mean loss, #correct]`` pair.
-        CUDA + arena-adopted training mode only."""
+        CUDA + arena-adopted training mode only.
+
+        ``hooks`` (optional, from the trainer): ``hooks.tail_grads_ready()`` is called as soon as the gradients of the
+        deep layers (``tail_split_prefix`` onwards: 88 % of a ResNet-18's parameters) are complete, so their optimizer
+        step can run beside the rest of the backward pass; ``hooks.before_tail_forward()`` is called before the first
+        forward use of those weights."""
         F = bnn.F
         if self.stats_workspace is not None:
             self.stats_workspace.zero_()
@@ -199,9 +206,12 @@ class ResNet(FederatedModule):
         cp = bnn.Ctx()
         h = bnn._MaxPoolFn.forward(cp, h, self.maxpool.k, self.maxpool.stride, self.maxpool.pad)
         tape = []
-        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+        for li, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
+            if li == 2 and hooks is not None:
+                hooks.before_tail_forward()
             for blk in layer:
                 h = self._block_fwd(blk, h, tape)
+        n_head_blocks = len(self.layer1) + len(self.layer2)
         ca = None
         if h.shape[1] == 1 and h.shape[2] == 1:
             feat = h.reshape(h.shape[0], h.shape[3])
@@ -217,10 +227,11 @@ class ResNet(FederatedModule):
         d = bnn._LinearFn.backward(cl, dlogits)[0]
         d = d.reshape(h.shape) if ca is None else bnn._AvgPoolFn.backward(ca, d)
         pieces = [d]
-        for entry in reversed(tape):
-            pieces = self._block_bwd(entry, pieces)
-        d = pieces[0] if len(pieces) == 1 else F.add(pieces[0], pieces[1])
-        d = bnn._MaxPoolFn.backward(cp, d)[0]
+        for bi in range(len(tape) - 1, -1, -1):
+            pieces = self._block_bwd(tape[bi], pieces)
+            if bi == n_head_blocks and hooks is not None:
+                hooks.tail_grads_ready()
+        d = bnn._MaxPoolFn.backward(cp, pieces[0], pieces[1] if len(pieces) > 1 else None)[0]
         _conv_bn_bwd(stem, d, needs_dx=False)
         bnn.WGRAD.join()
         return stats

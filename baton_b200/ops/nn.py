@@ -90,7 +90,17 @@ class _WgradOverlap:
         self.pending = False
         self.queued = False
 
-    def run(self, fn, *keep):
+    def mark(self, ref):
+        """Record "the operands are ready" on the current stream.  Calling this BEFORE the dgrad GEMM is enqueued and
+        :meth:`run` (with the returned token) AFTER it puts the dgrad kernel -- the one on the critical path -- first
+        in the captured graph's launch order while the weight-gradient branch still only depends on what precedes it."""
+        if not self.enabled or not ref.is_cuda:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(ref.device))
+        return ev
+
+    def run(self, fn, *keep, after=None):
         if not self.enabled or not keep[0].is_cuda:
             return fn()
         # dY[M, N] x X[M, K]: a GEMM that fills the machine on its own gains nothing from a parallel branch and
@@ -102,7 +112,10 @@ class _WgradOverlap:
         if side is None:
             side = self.streams[dev] = torch.cuda.Stream(device=dev)
         cur = torch.cuda.current_stream(dev)
-        side.wait_stream(cur)
+        if after is not None:
+            side.wait_event(after)
+        else:
+            side.wait_stream(cur)
         with torch.cuda.stream(side):
             fn()
         self.keep.append(keep)
@@ -350,22 +363,7 @@ class _ConvFn(torch.autograd.Function):
                 dx = F.gemm(dy2, wc, b_mn=True).view(n, 1, 1, c)
             return dx, gw, None, None, None, None, None, None, None
         igemm = getattr(ctx, "igemm", False)          # col IS x: the weight gradient gathers im2col(x) on the fly
-        if tgt is not None:
-            # the arena view is channels_last: physical [Cout, KH, KW, Cin] == [Cout, K]
-            out2d = tgt.permute(0, 2, 3, 1).reshape(cout, k_true) if tgt.dim() == 4 else tgt.view(cout, k_true)
-            assert out2d.data_ptr() == tgt.data_ptr(), "conv weight grad must be channels_last in the arena"
-            if igemm:
-                WGRAD.run(lambda: F.conv_igemm_wgrad_(dy2, col, out2d, kh, kw, stride, pad), dy2, col)
-            else:
-                WGRAD.run(lambda: F.gemm(dy2, col, a_mn=True, b_mn=True, out=out2d, accumulate=True, n_valid=k_true),
-                          dy2, col)
-        elif igemm:
-            g2 = torch.zeros((cout, k_true), dtype=torch.float32, device=dy.device)
-            F.conv_igemm_wgrad_(dy2, col, g2, kh, kw, stride, pad)
-            gw = g2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
-        else:
-            g2 = F.gemm(dy2, col, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True, n_valid=k_true)
-            gw = g2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
+        tok = WGRAD.mark(dy2)      # the weight-gradient branch depends on what is enqueued so far, not on the dgrad below
         dx = None
         if ctx.needs_dx:
             if (_CONV_IGEMM and _CONV_IGEMM_DGRAD and stride == 1 and kh == kw and kh > 1 and kp == k_true
@@ -378,6 +376,22 @@ class _ConvFn(torch.autograd.Function):
                     dx = dcol.view(n, h, w, c)
                 else:
                     dx = F.col2im(dcol, (n, h, w, c), kh, kw, stride, pad, ho, wo)
+        if tgt is not None:
+            # the arena view is channels_last: physical [Cout, KH, KW, Cin] == [Cout, K]
+            out2d = tgt.permute(0, 2, 3, 1).reshape(cout, k_true) if tgt.dim() == 4 else tgt.view(cout, k_true)
+            assert out2d.data_ptr() == tgt.data_ptr(), "conv weight grad must be channels_last in the arena"
+            if igemm:
+                WGRAD.run(lambda: F.conv_igemm_wgrad_(dy2, col, out2d, kh, kw, stride, pad), dy2, col, after=tok)
+            else:
+                WGRAD.run(lambda: F.gemm(dy2, col, a_mn=True, b_mn=True, out=out2d, accumulate=True, n_valid=k_true),
+                          dy2, col, after=tok)
+        elif igemm:
+            g2 = torch.zeros((cout, k_true), dtype=torch.float32, device=dy.device)
+            F.conv_igemm_wgrad_(dy2, col, g2, kh, kw, stride, pad)
+            gw = g2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
+        else:
+            g2 = F.gemm(dy2, col, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True, n_valid=k_true)
+            gw = g2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
         return dx, gw, None, None, None, None, None, None, None
 
 
@@ -549,10 +563,10 @@ class _MaxPoolFn(torch.autograd.Function):
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dy_b=None):
         (arg,) = ctx.saved_tensors
         shape, k, stride, pad = ctx.cfg
-        return F.maxpool_bwd(dy.contiguous(), arg, shape, k, stride, pad), None, None, None
+        return F.maxpool_bwd(dy.contiguous(), arg, shape, k, stride, pad, dy_b=dy_b), None, None, None
 
 
 class MaxPool2d(nn.Module):

@@ -92,19 +92,44 @@ class SeatedManagerPlane(ManagerPlane):
     ``nccl``).  ``aggregate`` turns the round's ``n_samples`` into a per-rank
     weight vector and POSTs it to every live seat; the seats run the collective
     kernel together.  The manager's own ``model`` is refreshed lazily through
-    ``Experiment.pull_global``."""
+    ``Experiment.pull_global``.
+
+    The manager stays the authority for two things the seats cannot agree on by themselves:
+
+    * the MODEL: a seat that has not been given the global model yet (first round after it registered -- including
+      a re-registration after an eviction -- or after the manager resumed from a checkpoint) receives the full
+      ``state_dict`` inside its ``round_start`` (reference behaviour, manager.py:77-86); synced seats get metadata only;
+    * the barrier EPOCH of the collective: every plan carries ``epoch`` = 3 x (aggregations dispatched so far), so a
+      seat that sat out rounds re-enters in step with its peers."""
 
     carries_tensors = False
 
-    def __init__(self, name: str = "fused", world_size: Optional[int] = None):
+    def __init__(self, name: str = "fused", world_size: Optional[int] = None, distribute_initial: bool = True):
         self.name = name
         self.world_size = world_size
+        self.distribute_initial = distribute_initial
+        self.n_aggregates = 0
 
     def round_start_message(self, model, update_name, n_epoch, extra=None) -> bytes:
         msg = {"update_name": update_name, "n_epoch": n_epoch, "dataplane": self.name}
         if extra:
             msg.update(extra)
         return wire.dumps(msg, prefer_json=True)
+
+    def unsynced(self, experiment, chosen) -> List[str]:
+        """Clients of this round that still need the global model."""
+        if not self.distribute_initial:
+            return []
+        cm = experiment.client_manager
+        return [c for c in chosen if c in cm.clients and not cm.clients[c].get("model_synced")]
+
+    def round_start_with_model(self, model, update_name, n_epoch, extra=None) -> bytes:
+        sd = model.state_dict()
+        sd = type(sd)((k, v.detach().to("cpu")) for k, v in sd.items())
+        msg = {"state_dict": sd, "update_name": update_name, "n_epoch": n_epoch, "dataplane": self.name}
+        if extra:
+            msg.update(extra)
+        return wire.dumps(msg)
 
     def rank_weights(self, experiment, responses) -> Dict[str, Any]:
         cm = experiment.client_manager
@@ -128,9 +153,12 @@ class SeatedManagerPlane(ManagerPlane):
         if sum(plan["n_samples_by_rank"]) <= 0:
             return False
         plan["update_name"] = experiment.update_manager.update_name
+        plan["epoch"] = 3 * self.n_aggregates
+        plan["round"] = self.n_aggregates
         body = wire.dumps(plan, prefer_json=True)
         cm = experiment.client_manager
         seats = [cid for cid, rec in cm.clients.items() if rec.get("rank") is not None]
+        self.n_aggregates += 1          # the epoch advances whether or not every seat answers
         result = await cm.notify_clients("aggregate", http_method="POST", data=body, clients=seats)
         ok = [cid for cid, r in result if r]
         log.info("aggregate dispatched to %d/%d seats", len(ok), len(seats))
@@ -194,11 +222,16 @@ class SeatedWorkerPlane(WorkerPlane):
                 "device": str(getattr(self.session, "device", "cpu"))}
 
     def receive_round(self, worker, msg) -> None:
-        # weights are already resident: the previous round's fused reduce wrote
-        # the new global model straight into this replica's arena (the
-        # reference's load_state_dict, worker.py:98, has nothing left to do)
-        if "state_dict" in msg:  # tolerate an http-style manager
+        # normally the weights are already resident: the previous round's fused reduce wrote the new global model
+        # straight into this replica's arena (the reference's load_state_dict, worker.py:98, has nothing left to do).
+        # The manager attaches the state_dict when this seat is new / rejoining / the manager resumed a checkpoint.
+        if "state_dict" in msg:
             worker.model.load_state_dict(msg["state_dict"])
+            arena = getattr(worker, "arena", None) or getattr(self.session, "arena", None)
+            if arena is not None:
+                arena.commit_global()       # these weights ARE the global model: refresh global_w + bf16 shadow
+            if hasattr(self.session, "stale"):
+                self.session.stale = False
 
     def update_message(self, worker, update_name, n_samples, loss_history) -> bytes:
         return wire.dumps({"n_samples": n_samples, "update_name": update_name,
@@ -206,7 +239,13 @@ class SeatedWorkerPlane(WorkerPlane):
                            "rank": self.rank, "dataplane": self.name}, prefer_json=True)
 
     def aggregate(self, worker, plan) -> None:
-        self.session.aggregate(plan["n_samples_by_rank"], plan.get("alive_ranks"))
+        kw = {}
+        if plan.get("epoch") is not None and hasattr(self.session, "epoch"):
+            kw["epoch"] = int(plan["epoch"])
+        self.session.aggregate(plan["n_samples_by_rank"], plan.get("alive_ranks"), **kw)
+        check = getattr(self.session, "check", None)
+        if check is not None:
+            check()             # a peer that died mid-collective surfaces here as an error, not as a hang
 
 
 def make_manager_plane(spec) -> ManagerPlane:

@@ -32,7 +32,7 @@ def _align(x: int, a: int) -> int:
 
 class FedAvgSession:
     def __init__(self, arena: ParamArena, group=None, *, wire_dtype: str = "bf16", mode: str = "delta",
-                 nvls: "bool | str" = "auto", n_ctas: int = 296, tile_elems: int = 0, timeout_log2: int = 0,
+                 nvls: "bool | str" = "auto", n_ctas: int = 296, tile_elems: int = 0, timeout_log2: int = 24,
                  reset_momentum: bool = True, tile_flags: bool = False):
         from ..ops._ext import load
         self._C = load()
@@ -46,6 +46,9 @@ class FedAvgSession:
         self.delta = mode == "delta"
         self.n_ctas = max(1, min(int(n_ctas), MAX_CTAS))
         self.tile_elems = int(tile_elems)
+        # every cross-GPU spin is BOUNDED by default (2^24 polls, several seconds): a seat that dies between the
+        # manager's plan and its launch turns into an error status on the survivors (check()), not into eight GPUs
+        # spinning forever -- the NCCL failure mode this data plane exists to avoid.  0 = spin without limit.
         self.timeout_log2 = int(timeout_log2)
         self.reset_momentum = reset_momentum
         self.off_wire = 0
@@ -61,6 +64,7 @@ class FedAvgSession:
             self.use_nvls = False      # the switch adds raw elements; block scales need the P2P path
         self.epoch = 0
         self.rounds = 0
+        self.stale = False          # True after a round this seat sat out: its weights are no longer the global model
         self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.loss_local = torch.zeros(MAX_LOSS, dtype=torch.float32, device=self.device)
         self.loss_out = torch.zeros(MAX_LOSS, dtype=torch.float32, device=self.device)
@@ -128,11 +132,18 @@ class FedAvgSession:
     # ------------------------------------------------------------------ the collective
     def aggregate(self, n_samples_by_rank: Optional[Sequence[float]] = None,
                   alive_ranks: Optional[Sequence[int]] = None, my_n: Optional[float] = None,
-                  loss_history: Optional[Sequence[float]] = None, on_side_stream: bool = False) -> None:
+                  loss_history: Optional[Sequence[float]] = None, on_side_stream: bool = False,
+                  epoch: Optional[int] = None) -> None:
         """Launch the fused reduce+broadcast+apply.  Either the full per-rank sample
         counts are given (manager-driven rounds: the plan comes over HTTP) or only this
-        rank's own count ``my_n`` (SPMD engine: peers' counts ride on the barrier flags)."""
+        rank's own count ``my_n`` (SPMD engine: peers' counts ride on the barrier flags).
+
+        ``epoch``: barrier epoch dictated by the manager's plan.  The manager is the single authority for it, so a
+        seat that sat out rounds (evicted, re-registered) re-enters in step with its peers instead of racing them
+        with a lagging counter."""
         world = self.world
+        if epoch is not None:
+            self.epoch = int(epoch) & 0xFFFFFFFF
         if n_samples_by_rank is not None:
             counts = [float(x) for x in n_samples_by_rank] + [0.0] * (world - len(n_samples_by_rank))
             counts = counts[:world]
@@ -144,7 +155,12 @@ class FedAvgSession:
             from_flags = True
         alive = list(range(world)) if alive_ranks is None else [int(r) for r in alive_ranks if 0 <= int(r) < world]
         if self.rank not in alive:
-            return  # this seat is not part of the round (it keeps its stale replica)
+            # not part of this round: the replica goes stale (``stale`` tells the worker to pull the global model
+            # before it takes part again) but the barrier epoch and the round counter keep pace with the peers
+            self.epoch = (self.epoch + 3) & 0xFFFFFFFF
+            self.rounds += 1
+            self.stale = True
+            return
         mask = 0
         for r in alive:
             mask |= 1 << r

@@ -93,6 +93,15 @@ class GraphedLocalSGD:
         self.input_dtype = input_dtype
         import os
         self.explicit = os.environ.get("BATON_EXPLICIT_STEP", "1") != "0"   # models that offer a hand-scheduled step
+        # optimizer slice of the deep layers beside the rest of the backward pass: implemented and validated, but measured
+        # neutral on B200 (the HBM-bound slice slows the latency-bound kernels it runs beside by as much as it
+        # hides: 4.52 vs 4.54 ms per 8 steps, profiles/r2_trace_sgd_overlap.txt) -> opt-in
+        self.tail_overlap = os.environ.get("BATON_SGD_OVERLAP", "0") == "1"
+        self.tail_ctas = int(os.environ.get("BATON_SGD_TAIL_CTAS", "148"))    # grid cap of the overlapped SGD slice
+        self._split = None
+        self._tail_stream = None
+        self._tail_pending = False
+        self._tail_done = False
         dev = arena.device
         self.device = dev
         self.hyper = torch.zeros(4, dtype=torch.float32, device=dev)
@@ -118,22 +127,67 @@ class GraphedLocalSGD:
         if ws is not None and not getattr(self.model, "zeroes_own_workspace", False):
             ws.zero_()
         explicit = getattr(self.model, "explicit_step", None) if self.explicit else None
+        a = self.arena
+        bf = a.theta_bf16
         if explicit is not None and self.loss_kind in ("ce", "cross_entropy"):
             # hand-scheduled forward + loss + backward (no autograd engine): two-piece block gradients, parallel shortcut
-            # branch; the loss kernel accumulates straight into the epoch's running sums
-            explicit(xb, yb, loss_acc=self.loss_acc)
-            stats = None
-        else:
-            out = self.model(xb)
-            loss, stats = self._loss(out, yb)
-            loss.backward()
-            self.bnn.WGRAD.join()      # weight-gradient GEMMs run on a side stream; they must land before the step
-        a = self.arena
+            # branch; the loss kernel accumulates straight into the epoch's running sums.  The optimizer step of the deep
+            # layers (their gradients are complete early in the backward pass) runs on a side stream beside the rest
+            # of the backward pass and the first layers of the NEXT step's forward.
+            split = self._tail_split()
+            self._tail_done = False
+            explicit(xb, yb, loss_acc=self.loss_acc, hooks=self if split else None)
+            end = split if (split and self._tail_done) else a.n_param
+            F.fused_sgd(a.theta[:end], a.grad[:end], self.hyper, a.momentum[:end] if a.momentum is not None else None,
+                        bf[:end] if bf is not None else None, zero_grad=True, nesterov=self.nesterov)
+            return
+        out = self.model(xb)
+        loss, stats = self._loss(out, yb)
+        loss.backward()
+        self.bnn.WGRAD.join()      # weight-gradient GEMMs run on a side stream; they must land before the step
         F.fused_sgd(a.theta[: a.n_param], a.grad, self.hyper, a.momentum,
-                    a.theta_bf16[: a.n_param] if a.theta_bf16 is not None else None,
-                    zero_grad=True, nesterov=self.nesterov)
-        if stats is not None:
-            self.loss_acc.add_(stats)
+                    bf[: a.n_param] if bf is not None else None, zero_grad=True, nesterov=self.nesterov)
+        self.loss_acc.add_(stats)
+
+    # ---- optimizer / backward overlap (hooks called by ``model.explicit_step``) ----
+    def _tail_split(self) -> int:
+        """Arena offset where the deep layers' parameters start (0: no split)."""
+        if not self.tail_overlap:
+            return 0
+        if self._split is None:
+            prefix = getattr(self.model, "tail_split_prefix", None)
+            self._split = 0
+            if prefix:
+                for name, slot in self.arena.slots.items():
+                    if slot.is_param and name.startswith(prefix):
+                        self._split = slot.offset - slot.offset % 8
+                        break
+        return self._split
+
+    def tail_grads_ready(self):
+        """Gradients of ``theta[split:n_param]`` are complete (once the weight-gradient branch has drained): run their
+        SGD slice on its own stream, on a capped grid, beside the remaining backward pass."""
+        a, dev, split = self.arena, self.device, self._split
+        if self._tail_stream is None:
+            self._tail_stream = torch.cuda.Stream(device=dev)
+        side = self._tail_stream
+        side.wait_stream(torch.cuda.current_stream(dev))
+        wg = self.bnn.WGRAD.streams.get(dev)
+        if wg is not None:
+            side.wait_stream(wg)
+        bf = a.theta_bf16
+        with torch.cuda.stream(side):
+            self.F.fused_sgd(a.theta[split: a.n_param], a.grad[split:], self.hyper,
+                             a.momentum[split:] if a.momentum is not None else None,
+                             bf[split: a.n_param] if bf is not None else None, zero_grad=True, nesterov=self.nesterov,
+                             max_ctas=self.tail_ctas)
+        self._tail_done = True
+        self._tail_pending = True
+
+    def before_tail_forward(self):
+        if self._tail_pending:
+            torch.cuda.current_stream(self.device).wait_stream(self._tail_stream)
+            self._tail_pending = False
 
     def _set_hyper(self, lr, momentum, weight_decay, dampening=0.0):
         vals = (float(lr), float(momentum), float(weight_decay), float(dampening))
@@ -154,6 +208,7 @@ class GraphedLocalSGD:
             snap_m = self.arena.momentum.clone() if self.arena.momentum is not None else None
             for _ in range(2):
                 self._step(X, y, perm[:batch_size])
+            self.before_tail_forward()       # drain the overlapped optimizer slice
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         from .ops._ext import total_launches
@@ -162,6 +217,7 @@ class GraphedLocalSGD:
         with torch.cuda.graph(graph):
             for s in range(n_steps):
                 self._step(X, y, perm[s * batch_size:(s + 1) * batch_size])
+            self.before_tail_forward()       # every forked stream must rejoin before the capture ends
         self.kernels_per_epoch = total_launches() - c0      # our kernels inside one epoch graph
         self.n_kernels_per_step = self.kernels_per_epoch // max(1, n_steps)
         # undo the side effects of warm-up + capture-time execution (capture does not execute,
@@ -208,6 +264,7 @@ class GraphedLocalSGD:
                 if tail:
                     with torch.enable_grad():
                         self._step(X, y, perm_full[n_steps * batch_size:])
+                    self.before_tail_forward()
                 epoch_losses[e].copy_(self.loss_acc)
         else:
             perm_full = torch.randperm(n, device=self.device)
@@ -218,6 +275,7 @@ class GraphedLocalSGD:
                 for idx in torch.split(perm_full, batch_size):
                     with torch.enable_grad():
                         self._step(X, y, idx)
+                self.before_tail_forward()
                 epoch_losses[e].copy_(self.loss_acc)
         steps = n_steps + (1 if tail else 0)
         self.last_steps = steps

@@ -49,6 +49,11 @@ def parse_args(argv=None):
     ap.add_argument("--backend", default="fused", choices=["fused", "nccl"])
     ap.add_argument("--n-ctas", type=int, default=296)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--api", default="engine", choices=["engine", "http"],
+                    help="http: drive the rounds through Manager + GpuExperimentWorker over HTTP (GET /start_round), "
+                         "one worker process per GPU and a CPU manager process -- Baton's API on the NVLink data plane")
+    ap.add_argument("--graph", action="store_true",
+                    help="--impl baseline only: CUDA-graph the stock model's local epoch + flat-buffer NCCL aggregate")
     ap.add_argument("--nvls", default="auto")
     ap.add_argument("--logical-clients", type=int, default=0,
                     help="> n_gpus: time-slice this many logical clients over the GPUs (sampling sweep config)")
@@ -124,6 +129,10 @@ def main(argv=None):
         os.execv(sys.executable, [sys.executable, os.path.join(ROOT, "baseline", "nccl_fedavg.py")] + sys.argv[1:])
 
     real_stdout = _claim_stdout()
+    if args.api == "http":
+        sys.path.insert(0, ROOT)
+        from baton_b200.apibench import main_http
+        return main_http(args, lambda obj: _emit(real_stdout, obj))
     import torch
     import torch.distributed as dist
 
