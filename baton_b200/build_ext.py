@@ -33,7 +33,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 if os.environ.get("BATON_BUILD_PHASE_TIMING") == "1":     # in-kernel %globaltimer stamps in the FedAvg collective
     NVCC_FLAGS.append("-DB200_FEDAVG_PHASE_TIMING")
 if TRACE:
-    NVCC_FLAGS.append("-DB200_TRACE")
+    NVCC_FLAGS += ["-DB200_TRACE", "-DB200_FEDAVG_PHASE_TIMING"]    # kernel timeline + in-kernel phase stamps of the collective
 
 
 def _nvcc() -> str:

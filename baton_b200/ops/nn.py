@@ -733,9 +733,9 @@ class _AttnFn(torch.autograd.Function):
     gradients are addressed in place through 4-D TMA maps (no head split / merge copies)."""
 
     @staticmethod
-    def forward(ctx, qkv, B, S, H, dh):
+    def forward(ctx, qkv, B, S, H, dh, mask_bias=None):
         D = H * dh
-        if _FUSED_ATTN and S == 128 and dh == 64:
+        if _FUSED_ATTN and S == 128 and dh == 64 and mask_bias is None:
             # experimental single-kernel forward (csrc/attention.cu): scores stay in TMEM, P is written once
             probs = torch.empty((B * H * S, S), dtype=BF16, device=qkv.device)
             out = torch.empty((B * S, D), dtype=BF16, device=qkv.device)
@@ -748,6 +748,8 @@ class _AttnFn(torch.autograd.Function):
         F.gemm_batched(q, k, scores, M=S, N=S, K=dh, lda=3 * D, ldb=3 * D, ldd=S, a_mn=False, b_mn=False,
                        n_outer=B, n_inner=H, a_strides=(S * 3 * D, dh), b_strides=(S * 3 * D, dh),
                        d_strides=(H * S * S, S * S), alpha=1.0 / math.sqrt(dh))
+        if mask_bias is not None:        # additive key-padding mask [B, S] (0 / large negative), broadcast over heads and queries
+            scores.view(B, H, S, S).add_(mask_bias.to(scores.dtype).view(B, 1, 1, S))
         probs = torch.empty_like(scores)
         load().softmax_fwd(scores, probs, B * H * S, S, 1.0)
         out = torch.empty((B * S, D), dtype=BF16, device=qkv.device)
@@ -756,6 +758,7 @@ class _AttnFn(torch.autograd.Function):
                        d_strides=(S * D, dh))
         ctx.save_for_backward(qkv, probs)
         ctx.dims = (B, S, H, dh)
+        ctx.masked = mask_bias is not None
         return out
 
     @staticmethod
@@ -765,10 +768,10 @@ class _AttnFn(torch.autograd.Function):
         D = H * dh
         dout = dout.contiguous()
         dqkv = torch.empty_like(qkv)
-        if _FUSED_ATTN and S == 128 and dh == 64:
+        if _FUSED_ATTN and S == 128 and dh == 64 and not getattr(ctx, "masked", False):
             # experimental single-kernel backward (csrc/attention.cu): dP / dS never leave the SM
             if load().attention_bwd(qkv, dout, probs, dqkv, B, S, H, dh, 1.0 / math.sqrt(dh)):
-                return dqkv, None, None, None, None
+                return dqkv, None, None, None, None, None
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
         dq, dk, dv = dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:]
         bh = (H * S * S, S * S)
@@ -788,17 +791,21 @@ class _AttnFn(torch.autograd.Function):
                        n_outer=B, n_inner=H, a_strides=bh, b_strides=pk, d_strides=pk, alpha=alpha)
         F.gemm_batched(dscores, q, dk, M=S, N=dh, K=S, lda=S, ldb=3 * D, ldd=3 * D, a_mn=True, b_mn=True,
                        n_outer=B, n_inner=H, a_strides=bh, b_strides=pk, d_strides=pk, alpha=alpha)
-        return dqkv, None, None, None, None
+        return dqkv, None, None, None, None, None
 
 
-def attention(qkv: torch.Tensor, B: int, S: int, H: int, dh: int) -> torch.Tensor:
-    """``softmax(Q K^T / sqrt(dh)) V`` for packed ``qkv [B*S, 3*H*dh]`` -> ``[B*S, H*dh]``."""
+def attention(qkv: torch.Tensor, B: int, S: int, H: int, dh: int, mask_bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``softmax(Q K^T / sqrt(dh) + mask_bias) V`` for packed ``qkv [B*S, 3*H*dh]`` -> ``[B*S, H*dh]``.
+    ``mask_bias``: optional additive key mask ``[B, S]`` (0 = attend, large negative = padding)."""
     if not qkv.is_cuda:
         D = H * dh
         q, k, v = (t.reshape(B, S, H, dh).transpose(1, 2) for t in qkv.split(D, dim=-1))
-        p = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh), dim=-1)
+        sc = q @ k.transpose(-1, -2) / math.sqrt(dh)
+        if mask_bias is not None:
+            sc = sc + mask_bias.to(sc.dtype).view(B, 1, 1, S)
+        p = torch.softmax(sc, dim=-1)
         return (p @ v).transpose(1, 2).reshape(B * S, D)
-    return _AttnFn.apply(qkv.contiguous(), B, S, H, dh)
+    return _AttnFn.apply(qkv.contiguous(), B, S, H, dh, mask_bias)
 
 
 class _EmbedFn(torch.autograd.Function):
