@@ -46,6 +46,9 @@ def main_http(args, emit) -> int:
     torch.cuda.set_device(dev)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+    # driver-level barriers go through GLOO: an NCCL barrier kernel parked on a worker GPU while rank 0 drives the round
+    # would sit beside the fused collective (which needs its whole grid co-resident) and wait for rank 0 -- a cycle
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
     name = "resnet18"
     mport = int(os.environ.get("BATON_API_PORT", "18080"))
     wport = mport + 1 + rank
@@ -57,8 +60,9 @@ def main_http(args, emit) -> int:
     h2d = X_host.numel() * X_host.element_size() + y_host.numel() * y_host.element_size()
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.barrier(group=host_group)
         torch.cuda.synchronize()
 
     manager_proc = None
@@ -97,7 +101,8 @@ def main_http(args, emit) -> int:
         w = GpuExperimentWorker(app, model, "127.0.0.1:{}".format(mport), device=dev, shard_fn=lambda: (X_host, y_host),
                                 backend=args.backend, wire_dtype=args.wire, port=wport, heartbeat_time=600,
                                 worker_host="http://127.0.0.1:{}/{}/".format(wport, name),
-                                train_kwargs={"lr": args.lr, "batch_size": args.batch_size}, n_ctas=args.n_ctas)
+                                train_kwargs={"lr": args.lr, "batch_size": args.batch_size},
+                                n_ctas=min(args.n_ctas, 148))     # one CTA per SM: slack for foreign kernels
         runner = web.AppRunner(app)
         await runner.setup()
         await web.TCPSite(runner, "127.0.0.1", wport).start()
@@ -145,14 +150,14 @@ def main_http(args, emit) -> int:
             emit({"api": "http", "error": "round failed: {!r}".format(exc)})
         os._exit(1)
     train_s = sum(getattr(w, "train_seconds", []) or [0.0])
-    t = torch.tensor([dt, train_s], device=dev, dtype=torch.float64)
+    t = torch.tensor([dt, train_s], dtype=torch.float64)
     # every seat must hold the same global model now: checksum the arena
-    chk = w.arena.theta[: w.arena.n].double().sum().reshape(1)
+    chk = w.arena.theta[: w.arena.n].double().sum().reshape(1).cpu()
     lo, hi = chk.clone(), chk.clone()
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=host_group)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=host_group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=host_group)
     dt, train_s = float(t[0]), float(t[1])
     if rank == 0:
         total = world * args.samples * args.local_epochs * args.steps

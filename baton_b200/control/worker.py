@@ -110,6 +110,21 @@ class ExperimentWorker:
             await self._session.close()
         self._executor.shutdown(wait=False, cancel_futures=True)
 
+    def rebind(self, app: web.Application) -> None:
+        """Attach this worker (model, data plane and all) to a fresh aiohttp application after its previous HTTP
+        front-end was shut down -- a seat coming back after a crash of its web process keeps its GPU state.  The caller
+        starts the site and calls :meth:`register_with_manager`; the manager hands out a new client id."""
+        self.app = app
+        self.client_id = self.key = None
+        self.update_in_progress = False
+        self._round_task = None
+        self._heartbeat_manager = None
+        self._executor = ThreadPoolExecutor(max_workers=1, thread_name_prefix="baton-train",
+                                            initializer=self._bind_device)
+        self._auto_register = False
+        self.register_handlers()
+        app.on_cleanup.append(self._on_cleanup)
+
     def _get_session(self) -> aiohttp.ClientSession:
         if self._session is None or self._session.closed:
             self._session = aiohttp.ClientSession()

@@ -52,7 +52,7 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::opt
           int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd, bool a_mn, bool b_mn, int64_t act,
           int64_t split_k, bool accumulate, double alpha, const std::optional<at::Tensor>& flags, int64_t flag_epoch,
           int64_t flag_elem_off, int64_t flag_tile_elems, int64_t flag_bias_off, int64_t force_bn, bool simt,
-          const std::optional<at::Tensor>& col_stats) {
+          const std::optional<at::Tensor>& col_stats, const std::optional<at::Tensor>& flag_epoch_word) {
   CHECK_CUDA(a); CHECK_CUDA(b); CHECK_CUDA(d);
   TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16, "gemm operands must be bf16");
   TORCH_CHECK(d.scalar_type() == at::kBFloat16 || d.scalar_type() == at::kFloat, "gemm output must be bf16/fp32");
@@ -70,7 +70,8 @@ void gemm(const at::Tensor& a, const at::Tensor& b, at::Tensor d, const std::opt
   check(b200_gemm_bf16(cptr(a), cptr(b), ptr(d), bp, M, N, K, lda, ldb, ldd, a_mn, b_mn, out_fp32, act, split_k,
                        accumulate, static_cast<float>(alpha), opt_ptr<const uint32_t>(flags),
                        static_cast<uint32_t>(flag_epoch), flag_elem_off, static_cast<int>(flag_tile_elems), flag_bias_off,
-                       static_cast<int>(force_bn), opt_ptr<float>(col_stats), cur_stream()),
+                       static_cast<int>(force_bn), opt_ptr<float>(col_stats), opt_ptr<const uint32_t>(flag_epoch_word),
+                       cur_stream()),
         "gemm_bf16");
 }
 
@@ -210,13 +211,17 @@ void dequant_mx(const at::Tensor& q, const at::Tensor& sf, at::Tensor out, int64
 }
 
 void fused_sgd(at::Tensor w, at::Tensor g, const std::optional<at::Tensor>& mom, const std::optional<at::Tensor>& wb,
-               const at::Tensor& hyper, bool zero_grad, bool nesterov, int64_t max_ctas) {
+               const at::Tensor& hyper, bool zero_grad, bool nesterov, int64_t max_ctas,
+               const std::optional<at::Tensor>& wire_slot, const std::optional<at::Tensor>& pack_global,
+               const std::optional<at::Tensor>& pack_scale, int64_t n_pack, bool wire_fp32) {
   CHECK_CUDA(w);
   TORCH_CHECK(w.scalar_type() == at::kFloat && g.scalar_type() == at::kFloat && hyper.scalar_type() == at::kFloat);
   TORCH_CHECK(w.is_contiguous() && g.is_contiguous() && w.numel() == g.numel());
   const c10::cuda::CUDAGuard guard(w.device());
   check(b200_fused_sgd(w.data_ptr<float>(), g.data_ptr<float>(), opt_ptr<float>(mom), opt_ptr<void>(wb), w.numel(),
-                       hyper.data_ptr<float>(), zero_grad, nesterov, static_cast<int>(max_ctas), cur_stream()),
+                       hyper.data_ptr<float>(), zero_grad, nesterov, static_cast<int>(max_ctas),
+                       reinterpret_cast<const unsigned long long*>(opt_ptr<const int64_t>(wire_slot)),
+                       opt_ptr<const float>(pack_global), opt_ptr<const float>(pack_scale), n_pack, wire_fp32, cur_stream()),
         "fused_sgd");
 }
 
@@ -303,10 +308,14 @@ void embedding_bwd(const at::Tensor& dy, const at::Tensor& idx, at::Tensor grad)
                            grad.data_ptr<float>(), idx.numel(), static_cast<int>(dy.size(-1)), cur_stream()),
         "embedding_bwd");
 }
-void pad_rows(const at::Tensor& s, at::Tensor d, int64_t rows, int64_t k, int64_t kp) {
+void pad_rows(const at::Tensor& s, at::Tensor d, int64_t rows, int64_t k, int64_t kp,
+              const std::optional<at::Tensor>& flags, const std::optional<at::Tensor>& epoch_word, int64_t elem_off,
+              int64_t granule) {
   CHECK_CUDA(s);
   const c10::cuda::CUDAGuard guard(s.device());
-  check(b200_pad_rows_bf16(s.data_ptr(), d.data_ptr(), rows, k, kp, cur_stream()), "pad_rows");
+  check(b200_pad_rows_bf16(s.data_ptr(), d.data_ptr(), rows, k, kp, opt_ptr<const uint32_t>(flags),
+                           opt_ptr<const uint32_t>(epoch_word), elem_off, static_cast<int>(granule), cur_stream()),
+        "pad_rows");
 }
 
 // ---- fused FedAvg collective -------------------------------------------------------------------
@@ -319,7 +328,7 @@ void fedavg_allreduce(const std::vector<int64_t>& wire_ptrs, const std::vector<i
                       bool counts_from_flags, int64_t alive_mask, int64_t rank, int64_t world, int64_t wire_kind,
                       bool delta, bool use_nvls, int64_t epoch, const std::optional<at::Tensor>& tile_flags,
                       int64_t flag_value, int64_t tile_elems, int64_t n_ctas, int64_t timeout_log2,
-                      const std::optional<at::Tensor>& status, const std::optional<at::Tensor>& phase_ns) {
+                      const std::optional<at::Tensor>& status, const std::optional<at::Tensor>& phase_ns, bool prepacked) {
   CHECK_CUDA(theta);
   TORCH_CHECK(world <= B200_MAX_RANKS && static_cast<int64_t>(wire_ptrs.size()) == world &&
               static_cast<int64_t>(pad_ptrs.size()) == world && static_cast<int64_t>(n_samples.size()) == world);
@@ -358,6 +367,7 @@ void fedavg_allreduce(const std::vector<int64_t>& wire_ptrs, const std::vector<i
   a.flag_value = static_cast<uint32_t>(flag_value);
   a.tile_elems = static_cast<int>(tile_elems);
   a.timeout_log2 = static_cast<int>(timeout_log2);
+  a.prepacked = prepacked ? 1 : 0;
   a.status = opt_ptr<int>(status);
   a.phase_ns = nullptr;
   if (phase_ns.has_value()) {

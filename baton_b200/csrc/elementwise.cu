@@ -21,14 +21,34 @@ static inline int ew_grid(long long n_vec, int max_ctas = 148 * 8) {
 // One pass over {w, g, m}: g' = g + wd*w ; m = mu*m + (1-damp)*g' ; step = nesterov ? g' + mu*m : m ;
 // w -= lr*step ; g = 0 (so split-K wgrad GEMMs can red.add into it next step) ; bf16 shadow = bf16(w).
 // Hyper-parameters come from device memory so a captured CUDA graph can be replayed with a new lr.
+// K4 "emit the upload copy" (SURVEY 2.6): the LAST step of a local epoch can also write this client's wire copy for the
+// round-end collective -- bf16 / fp32 of (w_new - global) * scale -- while w_new is still in registers, so the
+// collective's own pack phase (one more read of theta + global, ~10 B / element) disappears.  The wire address is
+// read from a device word (`wire_slot`): the collective double-buffers its wire by round parity and the captured
+// epoch graph must follow without being re-captured.  Elements [n, n_pack) are float BUFFERS (BatchNorm running
+// statistics): not optimised, only packed.
+struct SgdPack {
+  const unsigned long long* wire_slot;   // device word holding the wire base address, or nullptr = no pack
+  const float* global_w;                 // delta upload: wire = w - global_w; nullptr: wire = w
+  const float* scale;                    // device scalar multiplied into the wire value (NVLS: n_k; P2P: 1)
+  long long n_pack;                      // elements to pack (>= n)
+  int wire_fp32;                         // 0: bf16 wire, 1: fp32 wire
+};
+
 __global__ void __launch_bounds__(EW_THREADS)
 fused_sgd_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict__ mom,
                  __nv_bfloat16* __restrict__ wb, long long n, const float* __restrict__ hyper, int zero_grad,
-                 int nesterov) {
+                 int nesterov, const SgdPack pk) {
   griddep_launch_dependents();
   griddep_wait();
   const float lr = hyper[0], mu = hyper[1], wd = hyper[2], damp = hyper[3];
   const long long nv = n >> 2;
+  uint8_t* wire = nullptr;
+  float pscale = 1.f;
+  if (pk.wire_slot != nullptr) {
+    wire = reinterpret_cast<uint8_t*>(*pk.wire_slot);
+    if (pk.scale != nullptr) pscale = *pk.scale;
+  }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float4 wv = reinterpret_cast<float4*>(w)[i];
@@ -54,6 +74,30 @@ fused_sgd_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict
     reinterpret_cast<float4*>(w)[i] = wv;
     if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (wb != nullptr) reinterpret_cast<uint2*>(wb)[i] = make_uint2(pack_bf16x2(wv.x, wv.y), pack_bf16x2(wv.z, wv.w));
+    if (wire != nullptr) {
+      float4 d = wv;
+      if (pk.global_w != nullptr) {
+        const float4 gl = reinterpret_cast<const float4*>(pk.global_w)[i];
+        d.x -= gl.x; d.y -= gl.y; d.z -= gl.z; d.w -= gl.w;
+      }
+      d.x *= pscale; d.y *= pscale; d.z *= pscale; d.w *= pscale;
+      if (pk.wire_fp32) reinterpret_cast<float4*>(wire)[i] = d;
+      else reinterpret_cast<uint2*>(wire)[i] = make_uint2(pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
+    }
+  }
+  if (wire != nullptr) {      // float buffers behind the parameters: pack only (n and n_pack are multiples of 8)
+    const long long npv = pk.n_pack >> 2;
+    for (long long i = nv + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < npv;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      float4 d = reinterpret_cast<const float4*>(w)[i];
+      if (pk.global_w != nullptr) {
+        const float4 gl = reinterpret_cast<const float4*>(pk.global_w)[i];
+        d.x -= gl.x; d.y -= gl.y; d.z -= gl.z; d.w -= gl.w;
+      }
+      d.x *= pscale; d.y *= pscale; d.z *= pscale; d.w *= pscale;
+      if (pk.wire_fp32) reinterpret_cast<float4*>(wire)[i] = d;
+      else reinterpret_cast<uint2*>(wire)[i] = make_uint2(pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
+    }
   }
   // scalar tail (n is normally padded to a multiple of 4 by the arena)
   if (blockIdx.x == 0) {
@@ -352,9 +396,25 @@ gelu_bwd_vec_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, u
 }
 // dst[r, 0:kp] = src[r, 0:k] zero padded (weights whose K is not a multiple of 8, e.g. 7x7x3 = 147)
 __global__ void __launch_bounds__(EW_THREADS)
-pad_rows_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ d, long long rows, int k, int kp) {
-  griddep_launch_dependents();
+pad_rows_kernel(const __nv_bfloat16* __restrict__ s, __nv_bfloat16* __restrict__ d, long long rows, int k, int kp,
+                const uint32_t* __restrict__ flags, const uint32_t* __restrict__ epoch_word, long long elem_off, int granule) {
+  // gated mode: do NOT let the dependent GEMM become resident early -- its large CTAs would sit on the SMs while this
+  // kernel spins, and the collective that publishes the flags might be the one still waiting for those SMs
+  if (flags == nullptr) griddep_launch_dependents();
   griddep_wait();
+  if (flags != nullptr) {
+    // bcast_gemm staging: the source is a slice of the bf16 arena that the FedAvg collective may still be writing on
+    // another stream -- acquire the arrival flags of the granules under it first (bounded spin)
+    if (threadIdx.x == 0) {
+      const uint32_t need = *reinterpret_cast<const volatile uint32_t*>(epoch_word);
+      for (long long t = elem_off / granule; t <= (elem_off + rows * k - 1) / granule; ++t) {
+        unsigned long long spins = 0;
+        while (static_cast<int32_t>(ld_acquire_sys(flags + t) - need) < 0)
+          if (++spins > (1ull << 26)) break;
+      }
+    }
+    __syncthreads();
+  }
   const long long total = rows * kp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -391,10 +451,16 @@ using namespace b200;
 // max_ctas > 0 caps the grid (grid-stride kernel): an optimizer slice that runs BESIDE latency-bound compute kernels on
 // another stream must leave SM slots free for them
 extern "C" int b200_fused_sgd(float* w, float* g, float* mom, void* w_bf16, long long n, const float* hyper,
-                              int zero_grad, int nesterov, int max_ctas, cudaStream_t stream) {
+                              int zero_grad, int nesterov, int max_ctas, const unsigned long long* wire_slot,
+                              const float* pack_global, const float* pack_scale, long long n_pack, int wire_fp32,
+                              cudaStream_t stream) {
   if (n <= 0) return 0;
+  SgdPack pk;
+  pk.wire_slot = wire_slot; pk.global_w = pack_global; pk.scale = pack_scale;
+  pk.n_pack = n_pack > n ? n_pack : n; pk.wire_fp32 = wire_fp32;
+  if (wire_slot != nullptr && ((n & 7) || (pk.n_pack & 7))) return -2;
   launch_pdl(fused_sgd_kernel, max_ctas > 0 ? ew_grid(n >> 2, max_ctas) : ew_grid(n >> 2), EW_THREADS, 0, stream, w, g, mom, reinterpret_cast<__nv_bfloat16*>(w_bf16), n,
-                                                                hyper, zero_grad, nesterov);
+                                                                hyper, zero_grad, nesterov, pk);
   RET_LAST();
 }
 extern "C" int b200_weighted_sum(void* dst, const void* const* srcs, const float* weights, int n_src, long long n,
@@ -496,10 +562,13 @@ extern "C" int b200_gelu_bwd_bf16(const void* x, const void* dy, void* dx, long 
                                                          reinterpret_cast<__nv_bfloat16*>(dx), n);
   RET_LAST();
 }
-extern "C" int b200_pad_rows_bf16(const void* src, void* dst, long long rows, int k, int kp, cudaStream_t stream) {
+extern "C" int b200_pad_rows_bf16(const void* src, void* dst, long long rows, int k, int kp, const uint32_t* flags,
+                                  const uint32_t* epoch_word, long long elem_off, int granule, cudaStream_t stream) {
   if (rows <= 0) return 0;
+  if (flags != nullptr && (epoch_word == nullptr || granule <= 0)) return -2;
   launch_pdl(pad_rows_kernel, ew_grid(rows * kp), EW_THREADS, 0, stream, reinterpret_cast<const __nv_bfloat16*>(src),
-                                                                 reinterpret_cast<__nv_bfloat16*>(dst), rows, k, kp);
+                                                                 reinterpret_cast<__nv_bfloat16*>(dst), rows, k, kp, flags,
+                                                                 epoch_word, elem_off, granule);
   RET_LAST();
 }
 

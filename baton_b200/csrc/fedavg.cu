@@ -33,6 +33,8 @@
 // peer that dies mid-collective into an error status instead of a hang.
 #define B200_TU_TAG 7
 #include "pdl.cuh"
+#include <type_traits>
+
 #include "ptx.cuh"
 #include "launch.h"
 #include "mx.cuh"
@@ -40,6 +42,7 @@
 namespace b200 {
 
 constexpr int FEDAVG_THREADS = 512;
+constexpr int FLAG_GRANULE = 1024;   // elements covered by one arrival flag (bcast_gemm consumers)
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -189,7 +192,11 @@ __device__ __forceinline__ void phase_stamp(const FedAvgArgs& a, int slot) {
 }
 
 template <int WIRE>
-__global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(const __grid_constant__ FedAvgArgs a) {
+// One 512-thread CTA per SM, capped at 96 registers per thread (48 K of the SM's 64 K): the rest of the register file
+// stays available to small kernels of the NEXT round (batch gather, im2col, the flag-gated weight staging of
+// bcast_gemm) that are launched on the compute stream while this kernel is still running on its side stream -- and
+// a flag-gated consumer that became resident first can never keep this (cooperatively launched) grid from fitting.
+__global__ void __maxnreg__(96) fedavg_allreduce_kernel(const __grid_constant__ FedAvgArgs a) {
   using W = Wire<WIRE>;
   constexpr int VEC = W::VEC;
   constexpr bool SCALED = W::SCALED;
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
   // Loop bounds are warp-uniform (first lane's element) so the block-scale shuffles are legal.
   const float pack_scale = a.use_nvls ? my_n * a.nvls_prescale : 1.0f;
   phase_stamp(a, 0);                                   // start
-  if (my_n != 0.f || a.use_nvls) {
+  if ((my_n != 0.f || a.use_nvls) && !a.prepacked) {
     for (long long q = blockIdx.x; q * A < n_tiles; q += G) {
       for (int r = 0; r < A; ++r) {
         const long long t = q * A + r;
@@ -310,71 +317,110 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
   __syncthreads();
 
   // ---------------------------------------------------------------- phase 1: reduce + broadcast
-  for (long long t = my_pos + static_cast<long long>(blockIdx.x) * A; t < n_tiles; t += static_cast<long long>(G) * A) {
-    const long long base = t * T;
-    const int len = static_cast<int>((n - base) < T ? (n - base) : T);
-    for (int i = threadIdx.x * VEC; i - lane_elems < len; i += FEDAVG_THREADS * VEC) {
-      const bool valid = i < len;
-      const size_t off = (base + i) * esz;
-      const size_t sc_idx = sc_off + ((base + i) >> 5);
-      uint4 out;
-      if (!SCALED && a.use_nvls) {
-        if (valid) {
-          out = W::mc_reduce(reinterpret_cast<const uint8_t*>(a.wire_mc) + off);  // the switch adds the replicas
-          multimem_st_v4(reinterpret_cast<uint8_t*>(a.wire_mc) + off, out);       // the switch replicates the store
+  // A remote 16-byte load costs a full NVLink round trip (~2-3 us); with few ranks a thread that handles ONE wire vector
+  // per trip has only A loads in flight and the phase runs at a quarter of the link rate (2 GPUs: 54 us for 11 MB each
+  // way, phase stamps in profiles/r2_agg_phases_2gpu.txt).  Each trip therefore handles U vectors, U chosen so that
+  // about eight remote loads per thread are in flight whatever the number of ranks.
+  auto reduce_tiles = [&](auto u_tag) {
+    constexpr int U = decltype(u_tag)::value;
+    constexpr int KG = 8 / U;          // ranks per load group: U * KG = 8 wire vectors in flight per thread
+    for (long long t = my_pos + static_cast<long long>(blockIdx.x) * A; t < n_tiles; t += static_cast<long long>(G) * A) {
+      const long long base = t * T;
+      const int len = static_cast<int>((n - base) < T ? (n - base) : T);
+      constexpr int STEP = FEDAVG_THREADS * VEC;
+      for (int i0 = threadIdx.x * VEC; i0 - lane_elems < len; i0 += U * STEP) {
+        if (!SCALED && a.use_nvls) {
+          uint4 out[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * STEP;
+            if (i < len)      // the switch adds the replicas
+              out[u] = W::mc_reduce(reinterpret_cast<const uint8_t*>(a.wire_mc) + (base + i) * esz);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * STEP;
+            if (i < len)      // the switch replicates the store
+              multimem_st_v4(reinterpret_cast<uint8_t*>(a.wire_mc) + (base + i) * esz, out[u]);
+          }
+          continue;
         }
-      } else {
-        // peers in groups of 8 (one NVSwitch box): issue the group's loads first (memory-level
-        // parallelism), then accumulate in fixed rank order so the result is bitwise reproducible
-        float acc[VEC];
+        // peers in groups of 8 (one NVSwitch box): issue the group's loads first (memory-level parallelism), then
+        // accumulate in fixed rank order so the result is bitwise reproducible
+        float acc[U][VEC];
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-        if (valid) {
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[u][j] = 0.f;
 #pragma unroll 1
-          for (int k0 = 0; k0 < A; k0 += 8) {
-            uint4 v[8];
-            uint32_t sc[8];
+        for (int k0 = 0; k0 < A; k0 += KG) {
+          uint4 v[U][KG];
+          uint32_t sc[U][KG];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (k0 + k < A && s_w[k0 + k] != 0.f) {
-                v[k] = W::ld(s_wire[k0 + k] + off);
-                if constexpr (SCALED) sc[k] = ld_volatile_u8(s_wire[k0 + k] + sc_idx);
-              }
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * STEP;
+            if (i < len) {
+              const size_t off = (base + i) * esz;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if (k0 + k < A) {
-                const float w = s_w[k0 + k];
-                if (w != 0.f) {
-                  float f[VEC];
-                  float scale = 1.f;
-                  if constexpr (SCALED) scale = exp2_int(static_cast<int>(sc[k]) - 127);
-                  W::unpack(v[k], f, scale);
+              for (int k = 0; k < KG; ++k)
+                if (k0 + k < A && s_w[k0 + k] != 0.f) {
+                  v[u][k] = W::ld(s_wire[k0 + k] + off);
+                  if constexpr (SCALED) sc[u][k] = ld_volatile_u8(s_wire[k0 + k] + sc_off + ((base + i) >> 5));
+                }
+            }
+          }
 #pragma unroll
-                  for (int j = 0; j < VEC; ++j) acc[j] = fmaf(w, f[j], acc[j]);
+          for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * STEP;
+            if (i < len) {
+#pragma unroll
+              for (int k = 0; k < KG; ++k) {
+                if (k0 + k < A) {
+                  const float w = s_w[k0 + k];
+                  if (w != 0.f) {
+                    float f[VEC];
+                    float scale = 1.f;
+                    if constexpr (SCALED) scale = exp2_int(static_cast<int>(sc[u][k]) - 127);
+                    W::unpack(v[u][k], f, scale);
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) acc[u][j] = fmaf(w, f[j], acc[u][j]);
+                  }
                 }
               }
             }
           }
         }
-        float inv = 1.f;
-        int e = 0;
-        if constexpr (SCALED) {
-          e = quad_block_exponent<VEC>(acc);     // every lane of the warp arrives here
-          inv = exp2_int(-e);
-        }
-        if (valid) {
-          out = W::pack(acc, inv);
 #pragma unroll
-          for (int k = 0; k < B200_MAX_RANKS; ++k)
-            if (k < A) {
-              W::st_na(s_wire[k] + off, out);
-              if constexpr (SCALED)
-                if ((threadIdx.x & 3) == 0) st_volatile_u8(s_wire[k] + sc_idx, static_cast<uint32_t>(e + 127));
+        for (int u = 0; u < U; ++u) {
+          const int i = i0 + u * STEP;
+          const bool valid = i < len;
+          float inv = 1.f;
+          int e = 0;
+          if constexpr (SCALED) {
+            if (i - lane_elems < len) {                  // warp-uniform: every lane of the warp takes part in the shuffles
+              e = quad_block_exponent<VEC>(acc[u]);
+              inv = exp2_int(-e);
             }
+          }
+          if (valid) {
+            const size_t off = (base + i) * esz;
+            const uint4 out = W::pack(acc[u], inv);
+#pragma unroll
+            for (int k = 0; k < B200_MAX_RANKS; ++k)
+              if (k < A) {
+                W::st_na(s_wire[k] + off, out);
+                if constexpr (SCALED)
+                  if ((threadIdx.x & 3) == 0)
+                    st_volatile_u8(s_wire[k] + sc_off + ((base + i) >> 5), static_cast<uint32_t>(e + 127));
+              }
+          }
         }
       }
     }
-  }
+  };
+  if (A <= 2) reduce_tiles(std::integral_constant<int, 4>{});
+  else if (A <= 4) reduce_tiles(std::integral_constant<int, 2>{});
+  else reduce_tiles(std::integral_constant<int, 1>{});
   // weighted per-epoch loss (manager.py:127-130); every rank computes the same tiny vector
   if (blockIdx.x == 0 && a.loss_out != nullptr) {
     for (int e = threadIdx.x; e < a.n_loss; e += FEDAVG_THREADS) {
@@ -443,10 +489,14 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
         }
       }
       if (a.tile_flags != nullptr) {
+        // arrival flags have a FIXED granularity of FLAG_GRANULE elements (work tiles are multiples of it), so a consumer
+        // captured in a CUDA graph indexes them without knowing this round's tile size: flag[e / 1024] >= round means
+        // theta / global / bf16 shadow of elements [1024 f, 1024 f + 1024) carry the new global model
         __syncthreads();  // every thread's stores of this tile are done
-        if (threadIdx.x == 0) {
+        const int ng = (len + FLAG_GRANULE - 1) / FLAG_GRANULE;
+        for (int g = threadIdx.x; g < ng; g += FEDAVG_THREADS) {
           __threadfence();
-          st_release_sys(a.tile_flags + t, a.flag_value);
+          st_release_sys(a.tile_flags + base / FLAG_GRANULE + g, a.flag_value);
         }
       }
     }
@@ -463,11 +513,13 @@ __global__ void __launch_bounds__(FEDAVG_THREADS, 2) fedavg_allreduce_kernel(con
       a.int_local[i] = m;
     }
   }
-  // closing barrier: nobody may start the next round's phase 0 (overwriting its wire buffer, which
-  // peers pushed results into) or reuse int/loss wire pages while a peer still reads them
+  // No closing barrier: the wire buffer and the int / loss pages are DOUBLE-BUFFERED by round parity (the host passes
+  // the addresses of this round's half).  A rank that races ahead packs round r+1 into the other half while a slow
+  // peer still applies round r from this one; the half is reused in round r+2, and nobody can be there before every
+  // rank has passed barrier 2 of round r+1, i.e. has left round r altogether.  The pads hold monotone epochs
+  // (a faster rank's next-round arrival also satisfies this round's wait), so they need no parity.
   phase_stamp(a, 5);                                   // apply done
-  cta_barrier_all_ranks(a, a.epoch + 3, 0u, nullptr);
-  phase_stamp(a, 6);                                   // closing barrier passed
+  phase_stamp(a, 6);
 }
 
 // stand-alone cross-GPU barrier on the pads (one CTA): fences host-side phases
@@ -485,20 +537,43 @@ __global__ void flag_barrier_kernel(FedAvgArgs a, int slot) {
 
 }  // namespace b200
 
+// The kernel spins on cross-GPU flags per CTA, so every CTA of the grid must be resident at the same time or the ranks
+// deadlock each other.  It is therefore launched COOPERATIVELY: the runtime refuses a grid that cannot be co-resident
+// (cudaErrorCooperativeLaunchTooLarge) and schedules all CTAs together, also next to work on other streams -- instead
+// of the plain <<<>>> of round 1, which was only safe on an otherwise idle GPU.  The grid is clamped to what
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor allows on this device.
+template <int WIRE>
+static int launch_fedavg(const FedAvgArgs* args, int n_ctas, cudaStream_t stream) {
+  using namespace b200;
+  static int max_ctas = -1;
+  if (max_ctas < 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fedavg_allreduce_kernel<WIRE>, FEDAVG_THREADS, 0);
+    max_ctas = sms * per_sm;
+    if (max_ctas < 1) max_ctas = 1;
+  }
+  if (n_ctas > max_ctas) n_ctas = max_ctas;
+  void* kargs[] = {const_cast<FedAvgArgs*>(args)};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(fedavg_allreduce_kernel<WIRE>), dim3(n_ctas),
+                                              dim3(FEDAVG_THREADS), kargs, 0, stream);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int b200_fedavg_allreduce(const FedAvgArgs* args, int n_ctas, cudaStream_t stream) {
   using namespace b200;
   if (args->world > B200_MAX_RANKS || args->n % 8 != 0 || args->tile_elems % 8 != 0) return -2;
+  if (args->tile_flags != nullptr && args->tile_elems % FLAG_GRANULE != 0) return -2;
   if (n_ctas < 1) n_ctas = 1;
   if (args->wire_kind == 2) {
     // block-scaled fp8 wire: 32-element blocks must not straddle tiles, and the switch cannot rescale
     if (args->tile_elems % 32 != 0 || args->use_nvls) return -2;
-    fedavg_allreduce_kernel<2><<<n_ctas, FEDAVG_THREADS, 0, stream>>>(*args);
-  } else if (args->wire_kind == 1) {
-    fedavg_allreduce_kernel<1><<<n_ctas, FEDAVG_THREADS, 0, stream>>>(*args);
-  } else {
-    fedavg_allreduce_kernel<0><<<n_ctas, FEDAVG_THREADS, 0, stream>>>(*args);
+    return launch_fedavg<2>(args, n_ctas, stream);
   }
-  return static_cast<int>(cudaGetLastError());
+  if (args->wire_kind == 1) return launch_fedavg<1>(args, n_ctas, stream);
+  return launch_fedavg<0>(args, n_ctas, stream);
 }
 
 extern "C" int b200_flag_barrier(unsigned long long* const* pads, int rank, int world, uint32_t alive_mask,

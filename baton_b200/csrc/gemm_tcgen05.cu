@@ -72,7 +72,20 @@ struct GemmParams {
   int conv_cin;            // channels of the im2col-gathered tensor (multiple of 64): Cin forward, Cout for dgrad
   int conv_taps;           // dgrad: KH * KW
   int conv_ncol;           // dgrad: Cin of the convolution (column pitch of one tap inside a weight row)
+  const uint32_t* flag_epoch_ptr;   // bcast_gemm inside a captured graph: the required flag value lives in device memory
 };
+
+// Wait until every arrival flag covering arena elements [e0, e1] has reached `need` (published by the FedAvg kernel with
+// st.release.sys).  Bounded: a collective that died must not hang the consumer (it then reads what is there).
+__device__ __forceinline__ void wait_arrival_flags(const uint32_t* flags, long long e0, long long e1, int granule,
+                                                   uint32_t need) {
+  for (long long t = e0 / granule; t <= e1 / granule; ++t) {
+    unsigned long long spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(flags + t) - need) < 0) {
+      if (++spins > (1ull << 26)) break;
+    }
+  }
+}
 
 template <int BN>
 struct SmemLayout {
@@ -296,19 +309,13 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         // bcast_gemm: wait until the FedAvg kernel has published every arena tile under the rows
         // [n0, n0+BN) of the (K-major) weight matrix this CTA is about to TMA-load
         const int rows_here = (p.N - n0) < BN ? (p.N - n0) : BN;
-        const long long e0 = p.flag_elem_off + static_cast<long long>(n0) * p.ldb;
-        const long long e1 = p.flag_elem_off + static_cast<long long>(n0 + rows_here) * p.ldb - 1;
-        for (long long t = e0 / p.flag_tile_elems; t <= e1 / p.flag_tile_elems; ++t) {
-          while (ld_acquire_sys(p.tile_flags + t) < p.flag_epoch) {
-          }
-        }
-        if (p.flag_bias_off >= 0) {  // the bias slice the epilogue of this CTA will add
-          const long long b0 = p.flag_bias_off + n0, b1 = p.flag_bias_off + n0 + rows_here - 1;
-          for (long long t = b0 / p.flag_tile_elems; t <= b1 / p.flag_tile_elems; ++t) {
-            while (ld_acquire_sys(p.tile_flags + t) < p.flag_epoch) {
-            }
-          }
-        }
+        const uint32_t need = p.flag_epoch_ptr != nullptr ? *reinterpret_cast<const volatile uint32_t*>(p.flag_epoch_ptr)
+                                                          : p.flag_epoch;
+        wait_arrival_flags(p.tile_flags, p.flag_elem_off + static_cast<long long>(n0) * p.ldb,
+                           p.flag_elem_off + static_cast<long long>(n0 + rows_here) * p.ldb - 1, p.flag_tile_elems, need);
+        if (p.flag_bias_off >= 0)  // the bias slice the epilogue of this CTA will add
+          wait_arrival_flags(p.tile_flags, p.flag_bias_off + n0, p.flag_bias_off + n0 + rows_here - 1,
+                             p.flag_tile_elems, need);
         fence_proxy_async_all();  // order the acquires before the async-proxy (TMA) reads of global memory
       }
       for (int i = 0; i < num_kt; ++i) {
@@ -954,19 +961,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // bcast_gemm: wait until the FedAvg kernel has published every arena tile under the rows
         // [n0, n0+BN) of the (K-major) weight matrix this CTA is about to TMA-load
         const int rows_here = (p.N - n0) < BN ? (p.N - n0) : BN;
-        const long long e0 = p.flag_elem_off + static_cast<long long>(n0) * p.ldb;
-        const long long e1 = p.flag_elem_off + static_cast<long long>(n0 + rows_here) * p.ldb - 1;
-        for (long long t = e0 / p.flag_tile_elems; t <= e1 / p.flag_tile_elems; ++t) {
-          while (ld_acquire_sys(p.tile_flags + t) < p.flag_epoch) {
-          }
-        }
-        if (p.flag_bias_off >= 0) {  // the bias slice the epilogue of this CTA will add
-          const long long b0 = p.flag_bias_off + n0, b1 = p.flag_bias_off + n0 + rows_here - 1;
-          for (long long t = b0 / p.flag_tile_elems; t <= b1 / p.flag_tile_elems; ++t) {
-            while (ld_acquire_sys(p.tile_flags + t) < p.flag_epoch) {
-            }
-          }
-        }
+        const uint32_t need = p.flag_epoch_ptr != nullptr ? *reinterpret_cast<const volatile uint32_t*>(p.flag_epoch_ptr)
+                                                          : p.flag_epoch;
+        wait_arrival_flags(p.tile_flags, p.flag_elem_off + static_cast<long long>(n0) * p.ldb,
+                           p.flag_elem_off + static_cast<long long>(n0 + rows_here) * p.ldb - 1, p.flag_tile_elems, need);
+        if (p.flag_bias_off >= 0)  // the bias slice the epilogue of this CTA will add
+          wait_arrival_flags(p.tile_flags, p.flag_bias_off + n0, p.flag_bias_off + n0 + rows_here - 1,
+                             p.flag_tile_elems, need);
         fence_proxy_async_all();  // order the acquires before the async-proxy (TMA) reads of global memory
       }
       int s = 0;
@@ -1343,7 +1344,8 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
                               long long lda, long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act,
                               int split_k, int accumulate, float alpha, const uint32_t* tile_flags,
                               uint32_t flag_epoch, long long flag_elem_off, int flag_tile_elems,
-                              long long flag_bias_off, int force_bn, float* col_stats, cudaStream_t stream) {
+                              long long flag_bias_off, int force_bn, float* col_stats, const uint32_t* flag_epoch_ptr,
+                              cudaStream_t stream) {
   using namespace b200;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   // fused BatchNorm statistics: plain single-pass GEMM only (no split-K partials, no bias / activation / scaling)
@@ -1392,6 +1394,7 @@ extern "C" int b200_gemm_bf16(const void* a, const void* b, void* d, const float
   p.tile_flags = tile_flags; p.flag_epoch = flag_epoch; p.alpha = alpha;
   p.flag_elem_off = flag_elem_off; p.flag_tile_elems = flag_tile_elems; p.ldb = ldb;
   p.flag_bias_off = (tile_flags != nullptr && bias != nullptr) ? flag_bias_off : -1;
+  p.flag_epoch_ptr = tile_flags != nullptr ? flag_epoch_ptr : nullptr;
   p.batched = 0; p.batch_inner = 1; p.batch_count = 1; p.d_outer = 0; p.d_inner = 0;
   if (p.atomic_out && (!out_fp32 || bias != nullptr || act != 0)) return -3;
   const int max_stages = (bn == 256) ? 4 : (bn == 128 ? 6 : 8);
@@ -1473,7 +1476,7 @@ extern "C" int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int
   p.epi_staged = 0;
   p.col_stats = nullptr;
   p.tile_flags = nullptr; p.flag_epoch = 0; p.alpha = alpha; p.flag_elem_off = 0; p.flag_tile_elems = 0;
-  p.ldb = ldb; p.flag_bias_off = -1; p.stages = 4;
+  p.ldb = ldb; p.flag_bias_off = -1; p.flag_epoch_ptr = nullptr; p.stages = 4;
   p.batched = 1; p.batch_inner = n_inner; p.d_outer = d_outer; p.d_inner = d_inner;
   if (p.atomic_out && !out_fp32) return -3;
   dim3 grid((N + bn - 1) / bn, (M + BM - 1) / BM, n_outer * n_inner);
@@ -1529,7 +1532,7 @@ extern "C" int b200_conv_igemm_fwd(const void* x, const void* w, void* y, int N,
   p.a_mn = 0; p.b_mn = 0; p.k_tiles_per_split = per; p.cluster_k = cluster_k; p.atomic_out = 0;
   p.epi_staged = 0; p.col_stats = col_stats;
   p.tile_flags = nullptr; p.flag_epoch = 0; p.alpha = 1.0f; p.flag_elem_off = 0; p.flag_tile_elems = 0; p.ldb = K;
-  p.flag_bias_off = -1;
+  p.flag_bias_off = -1; p.flag_epoch_ptr = nullptr;
   p.batched = 0; p.batch_inner = 1; p.batch_count = 1; p.d_outer = 0; p.d_inner = 0;
   const int max_stages = (bn == 256) ? 4 : (bn == 128 ? 6 : 8);
   p.stages = per < max_stages ? (per < 2 ? 2 : per) : max_stages;
@@ -1578,7 +1581,7 @@ extern "C" int b200_conv_igemm_dgrad(const void* dy, const void* w, void* dx, in
   p.epi_staged = 0; p.col_stats = nullptr;
   p.tile_flags = nullptr; p.flag_epoch = 0; p.alpha = 1.0f; p.flag_elem_off = 0; p.flag_tile_elems = 0;
   p.ldb = static_cast<long long>(KH) * KW * Cin;
-  p.flag_bias_off = -1;
+  p.flag_bias_off = -1; p.flag_epoch_ptr = nullptr;
   p.batched = 0; p.batch_inner = 1; p.batch_count = 1; p.d_outer = 0; p.d_inner = 0;
   const int max_stages = (bn == 256) ? 4 : (bn == 128 ? 6 : 8);
   p.stages = per < max_stages ? (per < 2 ? 2 : per) : max_stages;
@@ -1622,7 +1625,7 @@ extern "C" int b200_conv_igemm_wgrad(const void* dy, const void* x, float* dw, i
   p.a_mn = 1; p.b_mn = 1; p.k_tiles_per_split = per; p.cluster_k = 1; p.atomic_out = 1;
   p.epi_staged = 0; p.col_stats = nullptr;
   p.tile_flags = nullptr; p.flag_epoch = 0; p.alpha = 1.0f; p.flag_elem_off = 0; p.flag_tile_elems = 0; p.ldb = Kc;
-  p.flag_bias_off = -1;
+  p.flag_bias_off = -1; p.flag_epoch_ptr = nullptr;
   p.batched = 0; p.batch_inner = 1; p.batch_count = 1; p.d_outer = 0; p.d_inner = 0;
   p.stages = 4;
   p.conv_ho = Ho; p.conv_wo = Wo; p.conv_stride = stride; p.conv_pad = pad; p.conv_kw = KW; p.conv_cin = Cin;

@@ -13,7 +13,8 @@ extern "C" {
 int b200_gemm_bf16(const void* a, const void* b, void* d, const float* bias, int M, int N, int K, long long lda,
                    long long ldb, long long ldd, int a_mn, int b_mn, int out_fp32, int act, int split_k, int accumulate,
                    float alpha, const uint32_t* tile_flags, uint32_t flag_epoch, long long flag_elem_off, int flag_tile_elems,
-                   long long flag_bias_off, int force_bn, float* col_stats, cudaStream_t stream);
+                   long long flag_bias_off, int force_bn, float* col_stats, const uint32_t* flag_epoch_ptr,
+                   cudaStream_t stream);
 int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int M, int N, int K, long long lda, long long ldb,
                            long long ldd, int a_mn, int b_mn, int out_fp32, int act, float alpha, int n_outer,
                            int n_inner, long long a_outer, long long a_inner, long long b_outer, long long b_inner,
@@ -48,8 +49,10 @@ int b200_gemm_simt(const void* a, const void* b, void* d, const float* bias, int
 
 // ---- elementwise.cu
 // hyper = device float[4] {lr, momentum, weight_decay, dampening}
+// wire_slot != nullptr: also emit the client's wire copy for the round-end collective (see SgdPack in elementwise.cu)
 int b200_fused_sgd(float* w, float* g, float* mom, void* w_bf16, long long n, const float* hyper, int zero_grad,
-                   int nesterov, int max_ctas, cudaStream_t stream);
+                   int nesterov, int max_ctas, const unsigned long long* wire_slot, const float* pack_global,
+                   const float* pack_scale, long long n_pack, int wire_fp32, cudaStream_t stream);
 int b200_weighted_sum(void* dst, const void* const* srcs, const float* weights, int n_src, long long n, int dtype,
                       cudaStream_t stream);  // dtype: 0 fp32, 1 bf16
 int b200_cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
@@ -65,7 +68,10 @@ int b200_gelu_bf16(const void* x, void* y, long long n, cudaStream_t stream);
 int b200_gelu_bwd_bf16(const void* x, const void* dy, void* dx, long long n, cudaStream_t stream);
 int b200_embedding_bwd(const void* dy, const long long* idx, float* grad, long long n_rows, int width,
                        cudaStream_t stream);
-int b200_pad_rows_bf16(const void* src, void* dst, long long rows, int k, int kp, cudaStream_t stream);
+// flags != nullptr: wait (bounded) until the arrival flags covering arena elements [elem_off, elem_off + rows * k) have
+// reached *epoch_word before reading src (bcast_gemm staging of a weight whose K is not TMA-aligned)
+int b200_pad_rows_bf16(const void* src, void* dst, long long rows, int k, int kp, const uint32_t* flags,
+                       const uint32_t* epoch_word, long long elem_off, int granule, cudaStream_t stream);
 
 // ---- fedavg.cu
 struct FedAvgArgs {
@@ -97,6 +103,7 @@ struct FedAvgArgs {
   uint32_t* tile_flags;             // optional local per-tile arrival flags (bcast_gemm) or nullptr
   uint32_t flag_value;              // value published into tile_flags
   int tile_elems;                   // arena tile size in elements
+  int prepacked;                    // 1: the wire already holds this round's upload (emitted by the last SGD step): skip phase 0
   int timeout_log2;                 // spin limit (2^k polls) before the kernel gives up, 0 = none
   int* status;                      // device int: set non-zero on barrier timeout
   unsigned long long* phase_ns;     // optional [16]: %globaltimer at the phase boundaries (first / last CTA), or nullptr

@@ -938,40 +938,56 @@ bn_bwd_cluster_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, 
 #pragma unroll
   for (int j = 0; j < 8; ++j) { m[j] = mean[c0 + j]; rs[j] = rstd[c0 + j]; }    // written two kernels ago at the latest
   griddep_wait();
-  float xh[ITER][8], g[ITER][8];
+  constexpr int NC = ITER > 0 ? ITER : 1;          // ITER == 0: rows are NOT cached (any row count): second pass re-reads
+  float xh[NC][8], g[NC][8];
   float sg[8], sgx[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sgx[j] = 0.f; }
+  auto load_row = [&](int r, float (&xh_)[8], float (&g_)[8]) {
+    const long long i = static_cast<long long>(r) * C8 + (c0 >> 3);
+    float xf[8];
+    unpack8_bn(x[i], xf);
+    unpack8_bn(dy_a[i], g_);
+    if (dy_b != nullptr) {
+      float t[8];
+      unpack8_bn(dy_b[i], t);
 #pragma unroll
-  for (int it = 0; it < ITER; ++it) {
-    const int r = r_begin + it * BNC_LANES + lane_r;
-    if (r < r_end) {
-      const long long i = static_cast<long long>(r) * C8 + (c0 >> 3);
-      float xf[8];
-      unpack8_bn(x[i], xf);
-      unpack8_bn(dy_a[i], g[it]);
-      if (dy_b != nullptr) {
-        float t[8];
-        unpack8_bn(dy_b[i], t);
+      for (int j = 0; j < 8; ++j) g_[j] += t[j];
+    }
+    if (relu) {
+      float yf[8];
+      unpack8_bn(y[i], yf);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[it][j] += t[j];
+      for (int j = 0; j < 8; ++j)
+        if (!(yf[j] > 0.f)) g_[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xh_[j] = (xf[j] - m[j]) * rs[j];
+  };
+  if constexpr (ITER > 0) {
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+      const int r = r_begin + it * BNC_LANES + lane_r;
+      if (r < r_end) {
+        load_row(r, xh[it], g[it]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sg[j] += g[it][j];
+          sgx[j] = fmaf(g[it][j], xh[it][j], sgx[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xh[it][j] = 0.f; g[it][j] = 0.f; }
       }
-      if (relu) {
-        float yf[8];
-        unpack8_bn(y[i], yf);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (!(yf[j] > 0.f)) g[it][j] = 0.f;
-      }
+    }
+  } else {
+    for (int r = r_begin + lane_r; r < r_end; r += BNC_LANES) {
+      load_row(r, xh[0], g[0]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        xh[it][j] = (xf[j] - m[j]) * rs[j];
-        sg[j] += g[it][j];
-        sgx[j] = fmaf(g[it][j], xh[it][j], sgx[j]);
+        sg[j] += g[0][j];
+        sgx[j] = fmaf(g[0][j], xh[0][j], sgx[j]);
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { xh[it][j] = 0.f; g[it][j] = 0.f; }
     }
   }
   // warp reduce over the 16 row lanes that share this chunk (lane bit 0 = chunk)
@@ -1028,18 +1044,26 @@ bn_bwd_cluster_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, 
     kb[j] = tot[chunk * 8 + j] * inv_rows;
     kc[j] = tot[16 + chunk * 8 + j] * inv_rows;
   }
+  auto store_row = [&](int r, const float (&xh_)[8], const float (&g_)[8]) {
+    const long long i = static_cast<long long>(r) * C8 + (c0 >> 3);
+    float o[8];
 #pragma unroll
-  for (int it = 0; it < ITER; ++it) {
-    const int r = r_begin + it * BNC_LANES + lane_r;
-    if (r < r_end) {
-      const long long i = static_cast<long long>(r) * C8 + (c0 >> 3);
-      float o[8];
+    for (int j = 0; j < 8; ++j) o[j] = ka[j] * (g_[j] - kb[j] - xh_[j] * kc[j]);
+    dx[i] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    if (dres != nullptr)
+      dres[i] = make_uint4(pack_bf16x2(g_[0], g_[1]), pack_bf16x2(g_[2], g_[3]), pack_bf16x2(g_[4], g_[5]),
+                           pack_bf16x2(g_[6], g_[7]));
+  };
+  if constexpr (ITER > 0) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = ka[j] * (g[it][j] - kb[j] - xh[it][j] * kc[j]);
-      dx[i] = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-      if (dres != nullptr)
-        dres[i] = make_uint4(pack_bf16x2(g[it][0], g[it][1]), pack_bf16x2(g[it][2], g[it][3]),
-                             pack_bf16x2(g[it][4], g[it][5]), pack_bf16x2(g[it][6], g[it][7]));
+    for (int it = 0; it < ITER; ++it) {
+      const int r = r_begin + it * BNC_LANES + lane_r;
+      if (r < r_end) store_row(r, xh[it], g[it]);
+    }
+  } else {
+    for (int r = r_begin + lane_r; r < r_end; r += BNC_LANES) {      // second pass: the slab is L2 (often L1) resident
+      load_row(r, xh[0], g[0]);
+      store_row(r, xh[0], g[0]);
     }
   }
   if (S > 1) cluster_wait_norm();
@@ -1170,7 +1194,7 @@ static int launch_bn_bwd_cluster(dim3 grid, int S, cudaStream_t stream, const ui
 }
 
 // Single-kernel BatchNorm backward (cluster per 16-channel slice).  dy = dy_a (+ dy_b); dgamma / dbeta are
-// ACCUMULATED.  Returns -2 when the shape does not fit (C % 16, more than 16 x 1024 rows): use reduce + apply.
+// ACCUMULATED.  Returns -2 when the shape does not fit (C % 16 != 0, misaligned pointers): use reduce + apply.
 extern "C" int b200_bn_bwd_cluster(const void* x, const void* y, const void* dy_a, const void* dy_b, void* dx, void* dres,
                                    const float* gamma, const float* save_mean, const float* save_rstd, float* dgamma,
                                    float* dbeta, long long rows, int C, int relu, int max_cluster, cudaStream_t stream) {
@@ -1186,7 +1210,6 @@ extern "C" int b200_bn_bwd_cluster(const void* x, const void* y, const void* dy_
   while (S > 1 && static_cast<long long>(slices) * S > 2 * 148) S >>= 1;          // ... within two CTAs per SM
   const int rpc = static_cast<int>((rows + S - 1) / S);
   const int iters = (rpc + BNC_LANES - 1) / BNC_LANES;
-  if (iters > 8) return -2;
   const dim3 grid(static_cast<unsigned>(slices), static_cast<unsigned>(S));
 #define BNC_GO(I)                                                                                                        \
   return launch_bn_bwd_cluster<I>(grid, S, stream, reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(y), \
@@ -1196,7 +1219,8 @@ extern "C" int b200_bn_bwd_cluster(const void* x, const void* y, const void* dy_
   if (iters <= 1) BNC_GO(1);
   if (iters <= 2) BNC_GO(2);
   if (iters <= 4) BNC_GO(4);
-  BNC_GO(8);
+  if (iters <= 8) BNC_GO(8);
+  BNC_GO(0);        // more rows than the register cache holds (ResNet stem: 32768 rows): two passes, still one kernel
 #undef BNC_GO
 }
 

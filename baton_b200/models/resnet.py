@@ -30,11 +30,13 @@ from .base import FederatedModule
 # gradient) that the consuming BatchNorm-backward kernel sums while loading, so the eight element-wise adds autograd
 # would launch per step disappear; the downsample branch runs as a parallel branch of the captured graph.
 # ---------------------------------------------------------------------------------------------------------------
-def _conv_bn_fwd(conv: "bnn.Conv2d", bn: "bnn.BatchNorm2d", x, residual=None):
+def _conv_bn_fwd(conv: "bnn.Conv2d", bn: "bnn.BatchNorm2d", x, residual=None, after_conv=None):
     cc, cb = bnn.Ctx(), bnn.Ctx()
     stats = conv._fusable_stats(x)
     z = bnn._ConvFn.forward(cc, x, conv.weight, conv._w_bf16(), conv.kernel_size, conv.kernel_size, conv.stride,
-                            conv.padding, None, stats)
+                            conv.padding, None, stats, conv.flags_cfg)
+    if after_conv is not None:
+        after_conv()
     y = bnn._BNFn.forward(cb, z, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
                           bn.eps, bn.momentum, bn.relu, True, bn.workspace, None, stats is not None)
     return y, (cc, cb)
@@ -202,12 +204,13 @@ class ResNet(FederatedModule):
         F = bnn.F
         if self.stats_workspace is not None:
             self.stats_workspace.zero_()
-        h, stem = _conv_bn_fwd(self.conv1, self.bn1, x)
+        h, stem = _conv_bn_fwd(self.conv1, self.bn1, x,
+                               after_conv=getattr(hooks, "after_first_gemm", None) if hooks is not None else None)
         cp = bnn.Ctx()
         h = bnn._MaxPoolFn.forward(cp, h, self.maxpool.k, self.maxpool.stride, self.maxpool.pad)
         tape = []
         for li, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
-            if li == 2 and hooks is not None:
+            if li == 2 and hooks is not None and getattr(hooks, "_tail_pending", False):
                 hooks.before_tail_forward()
             for blk in layer:
                 h = self._block_fwd(blk, h, tape)
@@ -229,7 +232,7 @@ class ResNet(FederatedModule):
         pieces = [d]
         for bi in range(len(tape) - 1, -1, -1):
             pieces = self._block_bwd(tape[bi], pieces)
-            if bi == n_head_blocks and hooks is not None:
+            if bi == n_head_blocks and hooks is not None and getattr(hooks, "_split", 0):
                 hooks.tail_grads_ready()
         d = bnn._MaxPoolFn.backward(cp, pieces[0], pieces[1] if len(pieces) > 1 else None)[0]
         _conv_bn_bwd(stem, d, needs_dx=False)

@@ -79,7 +79,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          act: int = 0, accumulate: bool = False, alpha: float = 1.0, split_k: Optional[int] = None,
          n_valid: Optional[int] = None, flags: Optional[torch.Tensor] = None, flag_epoch: int = 0,
          flag_elem_off: int = 0, flag_tile_elems: int = 0, flag_bias_off: int = -1, force_bn: int = 0,
-         force_simt: bool = False, col_stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+         force_simt: bool = False, col_stats: Optional[torch.Tensor] = None,
+         flag_epoch_word: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``out[M,N] = act(alpha * A @ B^T + bias)`` on tcgen05 tensor cores.
 
     ``n_valid`` limits the written columns (used when B carries zero K-padding
@@ -104,7 +105,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if use_simt:
         assert col_stats is None, "fused column statistics need the tensor-core path"
         C.gemm(a, b, out, bias, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, 1, accumulate, alpha, None, 0, 0, 0, -1, 0,
-               True, None)
+               True, None, None)
         return out
     bn = force_bn or pick_bn(M, N)
     if col_stats is not None:
@@ -119,7 +120,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if split_k > 1:
         assert out.dtype == torch.float32 and bias is None and act == 0
     C.gemm(a, b, out, bias, M, N, K, lda, ldb, ldd, a_mn, b_mn, act, split_k, accumulate, alpha, flags, flag_epoch,
-           flag_elem_off, flag_tile_elems, flag_bias_off, bn, False, col_stats)
+           flag_elem_off, flag_tile_elems, flag_bias_off, bn, False, col_stats, flag_epoch_word)
     return out
 
 
@@ -133,10 +134,17 @@ def gemm_stats_fusable(M: int, N: int, K: int) -> bool:
 # ---------------------------------------------------------------------------- elementwise / optimizer
 def fused_sgd(w: torch.Tensor, g: torch.Tensor, hyper: torch.Tensor, momentum_buf: Optional[torch.Tensor] = None,
               w_bf16: Optional[torch.Tensor] = None, zero_grad: bool = True, nesterov: bool = False,
-              max_ctas: int = 0) -> None:
+              max_ctas: int = 0, pack: Optional[dict] = None) -> None:
     """One kernel over the whole flat arena (reference: ``optimizer.step()``, demo.py:47).  ``max_ctas`` caps the
-    grid for a slice that runs concurrently with other work."""
-    load().fused_sgd(w, g, momentum_buf, w_bf16, hyper, zero_grad, nesterov, max_ctas)
+    grid for a slice that runs concurrently with other work.
+
+    ``pack`` ("emits the upload copy"): ``{"wire_slot": int64[1] device word holding the wire address,
+    "global_w": fp32 global copy or None, "scale": fp32[1] device scalar or None, "n_pack": elements to pack
+    (parameters + float buffers), "wire_fp32": bool}`` -- the step also writes this client's wire copy for the
+    round-end collective while the new weights are in registers."""
+    pk = pack or {}
+    load().fused_sgd(w, g, momentum_buf, w_bf16, hyper, zero_grad, nesterov, max_ctas, pk.get("wire_slot"),
+                     pk.get("global_w"), pk.get("scale"), int(pk.get("n_pack", 0)), bool(pk.get("wire_fp32", False)))
 
 
 def weighted_sum_(dst: torch.Tensor, srcs: Sequence[torch.Tensor], weights: Sequence[float]) -> torch.Tensor:
@@ -198,11 +206,15 @@ def gelu_bwd(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
     return dx
 
 
-def pad_rows(src2d: torch.Tensor, kp: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def pad_rows(src2d: torch.Tensor, kp: int, out: Optional[torch.Tensor] = None, gate: Optional[dict] = None) -> torch.Tensor:
+    """``gate`` (bcast_gemm): ``{"flags", "epoch_word", "elem_off", "tile_elems"}`` -- wait for the FedAvg collective's
+    arrival flags over the source slice of the bf16 arena before reading it."""
     rows, k = src2d.shape
     if out is None:
         out = torch.empty((rows, kp), dtype=BF16, device=src2d.device)
-    load().pad_rows(src2d, out, rows, k, kp)
+    g = gate or {}
+    load().pad_rows(src2d, out, rows, k, kp, g.get("flags"), g.get("epoch_word"), int(g.get("elem_off", 0)),
+                    int(g.get("tile_elems", 0)))
     return out
 
 

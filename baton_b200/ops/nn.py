@@ -204,9 +204,9 @@ class _LinearFn(torch.autograd.Function):
         x2 = x.reshape(-1, x.shape[-1])
         kw = {}
         if flags_cfg is not None:
-            kw = dict(flags=flags_cfg["flags"], flag_epoch=flags_cfg["epoch"], flag_elem_off=flags_cfg["elem_off"],
+            kw = dict(flags=flags_cfg["flags"], flag_epoch=flags_cfg.get("epoch", 0), flag_elem_off=flags_cfg["elem_off"],
                       flag_tile_elems=flags_cfg["tile_elems"], flag_bias_off=flags_cfg.get("bias_off", -1),
-                      force_bn=128)
+                      force_bn=128, flag_epoch_word=flags_cfg.get("epoch_word"))
         y = F.gemm(x2, w_bf16, bias=bias, act=act if act != 2 else 0,
                    out_dtype=torch.float32 if out_fp32 else BF16, **kw)
         ctx.act = act
@@ -283,7 +283,9 @@ class Linear(nn.Module):
         if getattr(self, "fp8", False) and self.act == 0 and self.bias is None and not self.out_fp32:
             y = matmul_fp8(x.reshape(-1, x.shape[-1]), self, _shadow(self, "weight", self.weight), self.in_features)
             return y.view(*x.shape[:-1], self.out_features)
-        cfg, self.flags_cfg = self.flags_cfg, None  # one-shot: only the first GEMM after a round is gated
+        cfg = self.flags_cfg
+        if cfg is not None and cfg.get("epoch_word") is None:
+            self.flags_cfg = None  # launch-constant epoch: one-shot, only the first GEMM after a round is gated
         return _LinearFn.apply(x, _wrap(self.weight, x), _wrap(self.bias, x), _shadow(self, "weight", self.weight),
                                self.act, self.out_fp32, cfg, _anchor(x, self.weight))
 
@@ -297,7 +299,8 @@ _CONV_IGEMM_DGRAD = __import__("os").environ.get("BATON_CONV_IGEMM_DGRAD", "1") 
 
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, w_bf16, kh, kw, stride, pad, anchor, stats=None):
+    def forward(ctx, x, weight, w_bf16, kh, kw, stride, pad, anchor, stats=None, gate=None):
+        """``gate``: bcast_gemm arrival-flag configuration of this layer's weights (first conv of the model only)."""
         weight = _unwrap(weight)
         n, h, w, c = x.shape
         cout = w_bf16.shape[0]
@@ -324,7 +327,11 @@ class _ConvFn(torch.autograd.Function):
             if y is None:
                 if not (kh == 1 and kw == 1 and stride == 1 and pad == 0 and c % 8 == 0):
                     col, ho, wo, kp = F.im2col(x, kh, kw, stride, pad)
-                y = F.gemm(col, w_bf16, col_stats=stats)
+                gk = {}
+                if gate is not None:     # the TMA producer acquires the arrival flags over this layer's weights
+                    gk = dict(flags=gate["flags"], flag_epoch_word=gate["epoch_word"], flag_elem_off=gate["elem_off"],
+                              flag_tile_elems=gate["tile_elems"], force_bn=F.pick_bn(col.shape[0], w_bf16.shape[0]))
+                y = F.gemm(col, w_bf16, col_stats=stats, **gk)
         ctx.save_for_backward(col, w_bf16)
         ctx.weight = weight
         ctx.geom = (n, h, w, c, kh, kw, stride, pad, ho, wo, kp)
@@ -361,7 +368,7 @@ class _ConvFn(torch.autograd.Function):
             if ctx.needs_dx:
                 wc = w_bf16.view(cout, kh * kw, c)[:, tap, :]
                 dx = F.gemm(dy2, wc, b_mn=True).view(n, 1, 1, c)
-            return dx, gw, None, None, None, None, None, None, None
+            return dx, gw, None, None, None, None, None, None, None, None
         igemm = getattr(ctx, "igemm", False)          # col IS x: the weight gradient gathers im2col(x) on the fly
         tok = WGRAD.mark(dy2)      # the weight-gradient branch depends on what is enqueued so far, not on the dgrad below
         dx = None
@@ -392,7 +399,7 @@ class _ConvFn(torch.autograd.Function):
         else:
             g2 = F.gemm(dy2, col, a_mn=True, b_mn=True, out_dtype=torch.float32, accumulate=True, n_valid=k_true)
             gw = g2.view(cout, kh, kw, c).permute(0, 3, 1, 2)
-        return dx, gw, None, None, None, None, None, None, None
+        return dx, gw, None, None, None, None, None, None, None, None
 
 
 class Conv2d(nn.Module):
@@ -407,6 +414,7 @@ class Conv2d(nn.Module):
         self.weight = nn.Parameter(w.contiguous(memory_format=torch.channels_last))
         self.k_true = kernel_size * kernel_size * in_channels
         self.kp = F.round_up(self.k_true, 8)
+        self.flags_cfg = None   # bcast_gemm: set by FedAvgSession.gate_first_conv for the first conv of the model
 
     def _w_bf16(self):
         sh = getattr(self, "weight_bf16", None)
@@ -414,7 +422,7 @@ class Conv2d(nn.Module):
             sh = _shadow(self, "weight", self.weight)
         sh = sh.view(self.out_channels, self.k_true)
         if self.kp != self.k_true:  # K not a multiple of 8 (7x7x3 stem): zero-padded copy for TMA
-            sh = F.pad_rows(sh, self.kp)
+            sh = F.pad_rows(sh, self.kp, gate=self.flags_cfg)
         return sh
 
     def forward(self, x):
@@ -425,7 +433,7 @@ class Conv2d(nn.Module):
             return conv2d_fp8(x, self)
         stats = self._fusable_stats(x)
         y = _ConvFn.apply(x, _wrap(self.weight, x), self._w_bf16(), self.kernel_size, self.kernel_size,
-                          self.stride, self.padding, _anchor(x, self.weight), stats)
+                          self.stride, self.padding, _anchor(x, self.weight), stats, self.flags_cfg)
         if stats is not None:
             y._bn_stats_ws = stats      # tells the BatchNorm that owns this workspace to skip its statistics pass
         return y

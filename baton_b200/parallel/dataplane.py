@@ -99,8 +99,8 @@ class SeatedManagerPlane(ManagerPlane):
     * the MODEL: a seat that has not been given the global model yet (first round after it registered -- including
       a re-registration after an eviction -- or after the manager resumed from a checkpoint) receives the full
       ``state_dict`` inside its ``round_start`` (reference behaviour, manager.py:77-86); synced seats get metadata only;
-    * the barrier EPOCH of the collective: every plan carries ``epoch`` = 3 x (aggregations dispatched so far), so a
-      seat that sat out rounds re-enters in step with its peers."""
+    * the ROUND INDEX of the collective: every plan carries ``round`` = aggregations dispatched so far, from which
+      every seat derives the same barrier epoch, so a seat that sat out rounds re-enters in step with its peers."""
 
     carries_tensors = False
 
@@ -153,8 +153,7 @@ class SeatedManagerPlane(ManagerPlane):
         if sum(plan["n_samples_by_rank"]) <= 0:
             return False
         plan["update_name"] = experiment.update_manager.update_name
-        plan["epoch"] = 3 * self.n_aggregates
-        plan["round"] = self.n_aggregates
+        plan["round"] = self.n_aggregates           # seats derive the collective's barrier epoch from it
         body = wire.dumps(plan, prefer_json=True)
         cm = experiment.client_manager
         seats = [cid for cid, rec in cm.clients.items() if rec.get("rank") is not None]
@@ -240,8 +239,8 @@ class SeatedWorkerPlane(WorkerPlane):
 
     def aggregate(self, worker, plan) -> None:
         kw = {}
-        if plan.get("epoch") is not None and hasattr(self.session, "epoch"):
-            kw["epoch"] = int(plan["epoch"])
+        if plan.get("round") is not None and hasattr(self.session, "base_epoch"):
+            kw["round_index"] = int(plan["round"])
         self.session.aggregate(plan["n_samples_by_rank"], plan.get("alive_ranks"), **kw)
         check = getattr(self.session, "check", None)
         if check is not None:

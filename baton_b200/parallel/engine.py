@@ -43,7 +43,7 @@ class RoundResult:
 class FederatedEngine:
     def __init__(self, model, device, *, backend: str = "fused", group=None, loss: str = "ce",
                  lr: float = 0.05, batch_size: int = 128, momentum: float = 0.0, weight_decay: float = 0.0,
-                 wire_dtype: str = "bf16", mode: str = "delta", n_ctas: int = 296, use_graph: bool = True,
+                 wire_dtype: str = "bf16", mode: str = "delta", n_ctas: int = 148, use_graph: bool = True,
                  logical_clients: int = 0, sample_k: Optional[int] = None, seed: int = 0, name: str = "exp",
                  nvls: "bool | str" = "auto", tile_flags: bool = False):
         self.device = torch.device(device)
@@ -67,6 +67,24 @@ class FederatedEngine:
                                tile_flags=tile_flags)
         self.backend = backend
         self.rank, self.world = self.session.rank, self.session.world
+        # K4: the last SGD step of the captured epoch writes the upload copy itself (no pack phase in the collective);
+        # only for the plain one-client-per-GPU rounds -- logical clients fold their deltas after training
+        self.prepack = (backend == "fused" and self.device.type == "cuda" and not (logical_clients and logical_clients > self.world)
+                        and __import__("os").environ.get("BATON_PREPACK", "1") != "0")
+        if self.prepack and hasattr(self.session, "pack_spec"):
+            self.trainer.pack = self.session.pack_spec()
+        # the round-end collective runs on the session's high-priority side stream: the NEXT round's host->device shard
+        # copy (and anything else that does not touch the arena) overlaps it; local training joins first
+        self.overlap_collective = (backend == "fused" and self.device.type == "cuda"
+                                   and __import__("os").environ.get("BATON_COLLECTIVE_OVERLAP", "1") != "0")
+        # K3 (bcast_gemm) on the flagship path: the first convolution's weight staging + GEMM acquire the collective's
+        # arrival flags, and the head of the next round's captured epoch runs while the collective is still in flight
+        self.k3 = bool(self.overlap_collective and tile_flags and hasattr(model, "conv1")
+                       and isinstance(self.session, FedAvgSession) and hasattr(self.session, "gate_first_conv")
+                       and hasattr(self.trainer, "k3_join"))
+        if self.k3:
+            self.session.gate_first_conv(model.conv1)
+            self.trainer.k3_join = self.sync
         self.hp = dict(lr=lr, batch_size=batch_size, momentum=momentum, weight_decay=weight_decay)
         self.n_rounds = 0
         self.logical_clients = logical_clients if logical_clients and logical_clients > self.world else 0
@@ -125,11 +143,16 @@ class FederatedEngine:
                 if not X.is_cuda:
                     with phase("baton.h2d_shard", self.phase_s):
                         X, y = self.stage(X, y)
+                if not self.k3:
+                    self.sync()              # the previous round's collective must have landed before training reads theta
+                if self.prepack and self.trainer.pack is not None:
+                    self.session.arm_prepack(float(X.shape[0]))
                 with phase("baton.local_train", self.phase_s):
                     losses_dev = self.trainer.run(X, y, n_epoch=n_epoch, return_device=True, **self.hp)
                 total_n = X.shape[0]
         else:
             # time-sliced logical clients: fold n_k * (theta_k - global) locally, then upload the mean
+            self.sync()
             if len(mine) > 1 and self._acc is None:
                 self._acc = torch.zeros_like(a.theta)
             if len(mine) > 1:
@@ -167,13 +190,23 @@ class FederatedEngine:
             hist = loss_for_wire.tolist()       # device -> host read of the round's result
         return RoundResult(update_name, int(total_n), hist, participants)
 
+    def sync(self) -> None:
+        """Make the compute stream wait for a collective that is still running on the side stream (call before
+        anything reads or writes the arena: training, ``state_dict()``, checkpoints)."""
+        join = getattr(self.session, "join", None)
+        if join is not None:
+            join()
+
     def _aggregate(self, my_n: float, loss_dev) -> None:
         s = self.session
+        side = bool(self.overlap_collective and isinstance(s, FedAvgSession))
         if loss_dev is not None and hasattr(s, "loss_local"):
             k = min(loss_dev.numel(), s.loss_local.numel())
             s.loss_local.zero_()
             s.loss_local[:k].copy_(loss_dev[:k])
-            s.aggregate(my_n=my_n)
+            pre = bool(self.prepack and getattr(self.trainer, "emitted_wire", False) and my_n > 0
+                       and not getattr(self.trainer, "last_had_tail_step", False))
+            s.aggregate(my_n=my_n, prepacked=pre, on_side_stream=side) if isinstance(s, FedAvgSession) else s.aggregate(my_n=my_n)
         elif loss_dev is not None:
             s.aggregate(my_n=my_n, loss_history=loss_dev.tolist())
         else:
@@ -183,4 +216,5 @@ class FederatedEngine:
         return self.session.reduced_loss(n_epoch)
 
     def state_dict(self):
+        self.sync()
         return self.model.state_dict()

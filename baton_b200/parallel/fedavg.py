@@ -23,7 +23,7 @@ from .arena import ParamArena
 from .symm import SymmetricBuffer
 
 MAX_LOSS = 64       # per-epoch loss slots carried through the collective
-MAX_CTAS = 296      # 2 resident CTAs per SM
+MAX_CTAS = 296      # pad slots; the kernel runs one 512-thread CTA per SM (148 on B200), clamped by the launcher
 
 
 def _align(x: int, a: int) -> int:
@@ -32,7 +32,7 @@ def _align(x: int, a: int) -> int:
 
 class FedAvgSession:
     def __init__(self, arena: ParamArena, group=None, *, wire_dtype: str = "bf16", mode: str = "delta",
-                 nvls: "bool | str" = "auto", n_ctas: int = 296, tile_elems: int = 0, timeout_log2: int = 24,
+                 nvls: "bool | str" = "auto", n_ctas: int = 148, tile_elems: int = 0, timeout_log2: int = 24,
                  reset_momentum: bool = True, tile_flags: bool = False):
         from ..ops._ext import load
         self._C = load()
@@ -51,10 +51,15 @@ class FedAvgSession:
         # spinning forever -- the NCCL failure mode this data plane exists to avoid.  0 = spin without limit.
         self.timeout_log2 = int(timeout_log2)
         self.reset_momentum = reset_momentum
+        # wire / int / loss pages exist TWICE (round parity): the kernel has no closing barrier, a rank that races ahead
+        # packs the next round into the other half while a slow peer still applies this one (csrc/fedavg.cu)
+        self.half_wire = _align(self.wire_bytes(), 2 << 20)          # multicast-friendly granularity
+        self.half_int = _align(max(arena.n_int, 1) * 8, 256)
+        self.half_loss = _align(MAX_LOSS * 4, 256)
         self.off_wire = 0
-        self.off_int = _align(self.wire_bytes(), 256)
-        self.off_loss = _align(self.off_int + max(arena.n_int, 1) * 8, 256)
-        self.off_pads = _align(self.off_loss + MAX_LOSS * 4, 256)
+        self.off_int = 2 * self.half_wire
+        self.off_loss = self.off_int + 2 * self.half_int
+        self.off_pads = _align(self.off_loss + 2 * self.half_loss, 256)
         total = _align(self.off_pads + (MAX_CTAS + 8) * self._C.MAX_RANKS * 8, 2 << 20)
         self.symm = SymmetricBuffer(total, self.device, group)
         self.rank, self.world = self.symm.rank, self.symm.world
@@ -72,17 +77,29 @@ class FedAvgSession:
         self.min_tile = 1024
         n_tiles = (arena.n + self.min_tile - 1) // self.min_tile
         self.tile_flags = torch.zeros(n_tiles, dtype=torch.int32, device=self.device) if tile_flags else None
+        # flag value consumers must wait for (= rounds launched so far): device-resident so captured graphs follow
+        self.epoch_word = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.last_tile_elems = self.tile_elems or self.min_tile
         # a high-priority stream lets the collective's CTAs become resident ahead of a flag-gated
         # GEMM that is launched right behind it on the compute stream
         self.stream = torch.cuda.Stream(device=self.device, priority=-1) if self.device.type == "cuda" else None
         self.symm.barrier()
+        # K4: the last SGD step of an epoch may write this rank's wire copy itself (ops.fused_sgd(pack=...)); the wire
+        # address of the upcoming round (parity half) and the pack scale live in device words so a captured graph follows
+        self.wire_slot = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.pack_scale = torch.ones(1, dtype=torch.float32, device=self.device)
+        self._armed_for = None     # (epoch, scale) the wire words were armed for
         self.phase_ns = None       # enable_phase_timing(): int64[16] of %globaltimer stamps written by the kernel
         self.nvls_choice = "forced" if nvls != "auto" else "default"
         if nvls == "auto" and self.use_nvls and self.delta and self.world > 1 and arena.global_w is not None:
             self.autotune_nvls()
+        # barrier epoch at the end of construction (the autotune above already ran collectives): identical on every rank,
+        # and the origin of the manager-dictated round index (aggregate(round_index=...))
+        self.base_epoch = self.epoch
 
-    PHASES = ("pack", "barrier1", "reduce_bcast", "barrier2", "apply", "barrier3")
+    FLAG_GRANULE = 1024        # elements per arrival flag (csrc/fedavg.cu)
+
+    PHASES = ("pack", "barrier1", "reduce_bcast", "barrier2", "apply", "exit")
 
     def enable_phase_timing(self) -> None:
         """Ask the kernel to record %globaltimer at its phase boundaries (first and last CTA) -- the way to
@@ -129,21 +146,44 @@ class FedAvgSession:
         self.check()
         self.symm.barrier()
 
+    # ------------------------------------------------------------------ K4: upload copy emitted by the optimizer
+    def pack_spec(self) -> Optional[dict]:
+        """Arguments for ``ops.fused_sgd(pack=...)`` (stable device tensors: safe to capture), or None when the wire
+        format needs the in-kernel pack (block-scaled fp8)."""
+        if self.wire_kind == 2 or self.device.type != "cuda":
+            return None
+        a = self.arena
+        return {"wire_slot": self.wire_slot, "global_w": a.global_w if self.delta else None, "scale": self.pack_scale,
+                "n_pack": a.n, "wire_fp32": self.wire_kind == 0}
+
+    def arm_prepack(self, my_n: float) -> None:
+        """Point the device words at the wire half of the UPCOMING round and set the pack scale (n_k under NVLS, where
+        the switch can only add; 1 for peer loads, which weight on the reader side).  Call before the local epoch(s)."""
+        par = (self.epoch // 3) & 1
+        addr = self.symm.peer_ptrs(self.off_wire + par * self.half_wire)[self.rank]
+        scale = float(my_n) if (self.use_nvls and self.world > 1) else 1.0
+        key = (self.epoch, scale)
+        if self._armed_for != key:
+            self.wire_slot.fill_(int(addr))
+            self.pack_scale.fill_(scale)
+            self._armed_for = key
+
     # ------------------------------------------------------------------ the collective
     def aggregate(self, n_samples_by_rank: Optional[Sequence[float]] = None,
                   alive_ranks: Optional[Sequence[int]] = None, my_n: Optional[float] = None,
                   loss_history: Optional[Sequence[float]] = None, on_side_stream: bool = False,
-                  epoch: Optional[int] = None) -> None:
+                  round_index: Optional[int] = None, prepacked: bool = False) -> None:
         """Launch the fused reduce+broadcast+apply.  Either the full per-rank sample
         counts are given (manager-driven rounds: the plan comes over HTTP) or only this
         rank's own count ``my_n`` (SPMD engine: peers' counts ride on the barrier flags).
 
-        ``epoch``: barrier epoch dictated by the manager's plan.  The manager is the single authority for it, so a
-        seat that sat out rounds (evicted, re-registered) re-enters in step with its peers instead of racing them
-        with a lagging counter."""
+        ``round_index``: number of aggregations the MANAGER has dispatched before this one.  The manager is the single
+        authority for it: the barrier epoch becomes ``base_epoch + 3 * round_index`` on every seat, so a seat that sat
+        out rounds (evicted, re-registered) re-enters in step with its peers instead of racing them with a lagging
+        counter (epochs must never run backwards: the pads keep the highest epoch ever seen)."""
         world = self.world
-        if epoch is not None:
-            self.epoch = int(epoch) & 0xFFFFFFFF
+        if round_index is not None:
+            self.epoch = (self.base_epoch + 3 * int(round_index)) & 0xFFFFFFFF
         if n_samples_by_rank is not None:
             counts = [float(x) for x in n_samples_by_rank] + [0.0] * (world - len(n_samples_by_rank))
             counts = counts[:world]
@@ -169,29 +209,44 @@ class FedAvgSession:
             self.loss_local.zero_()
             self.loss_local[:k].copy_(torch.tensor([float(x) for x in loss_history[:k]]), non_blocking=True)
         a = self.arena
+        # the optimizer's wire copy is only valid for the round / scale it was armed for and when the collective runs
+        # the way arm_prepack assumed (NVLS needs every rank alive); otherwise the kernel packs itself (always correct)
+        nvls_now = bool(self.use_nvls and len(alive) == world)
+        want_scale = (counts[self.rank] if not from_flags else float(my_n)) if (self.use_nvls and world > 1) else 1.0
+        prepacked = bool(prepacked and self.wire_kind != 2 and self._armed_for == (self.epoch, float(want_scale))
+                         and (nvls_now == bool(self.use_nvls and world > 1)))
+        self.last_prepacked = prepacked
         if self.tile_elems:
             tile = self.tile_elems
         else:   # one tile per (live rank, CTA): n / (A * G), rounded up to a multiple of 8 elements
             per = -(-a.n // (len(alive) * self.n_ctas))
             tile = max(self.min_tile, (per + 31) // 32 * 32)
+        if self.tile_flags is not None:      # arrival flags cover fixed 1024-element granules: tiles must not split one
+            tile = (tile + self.FLAG_GRANULE - 1) // self.FLAG_GRANULE * self.FLAG_GRANULE
         self.last_tile_elems = tile
         flag_value = self.rounds + 1
+        par = (self.epoch // 3) & 1            # round parity: which half of the wire / int / loss pages this round uses
+        o_wire, o_int, o_loss = (self.off_wire + par * self.half_wire, self.off_int + par * self.half_int,
+                                 self.off_loss + par * self.half_loss)
         cur = torch.cuda.current_stream(self.device)
         stream = self.stream if on_side_stream else cur
+        if self.tile_flags is not None:
+            self.epoch_word.fill_(flag_value)       # compute stream: whatever is enqueued after this call waits for THIS round
         if on_side_stream:
             stream.wait_stream(cur)
         with torch.cuda.stream(stream):
             self._C.fedavg_allreduce(
-                self.symm.peer_ptrs(self.off_wire), self.symm.peer_ptrs(self.off_pads),
-                self.symm.mc(self.off_wire) if self.use_nvls else 0,
+                self.symm.peer_ptrs(o_wire), self.symm.peer_ptrs(self.off_pads),
+                self.symm.mc(o_wire) if self.use_nvls else 0,
                 a.theta, a.global_w, a.theta_bf16,
                 a.momentum if self.reset_momentum else None,
                 a.int_arena if a.n_int > 0 else None,
-                self.symm.peer_ptrs(self.off_int) if a.n_int > 0 else [],
-                self.loss_local, self.symm.peer_ptrs(self.off_loss), self.loss_out,
+                self.symm.peer_ptrs(o_int) if a.n_int > 0 else [],
+                self.loss_local, self.symm.peer_ptrs(o_loss), self.loss_out,
                 counts, from_flags, mask, self.rank, world, self.wire_kind, self.delta,
                 bool(self.use_nvls and len(alive) == world), self.epoch,
-                self.tile_flags, flag_value, tile, self.n_ctas, self.timeout_log2, self.status, self.phase_ns)
+                self.tile_flags, flag_value, tile, self.n_ctas, self.timeout_log2, self.status, self.phase_ns,
+                prepacked)
         self.epoch = (self.epoch + 3) & 0xFFFFFFFF     # uint32 wrap: the kernel compares signed differences
         self.rounds += 1
         self._side_pending = on_side_stream
@@ -226,7 +281,25 @@ class FedAvgSession:
                 if s.is_param and self.arena._owner(name) is module and name.endswith(".bias"):
                     bias_off = s.offset
         module.flags_cfg = {"flags": self.tile_flags, "epoch": self.rounds, "elem_off": slot.offset,
-                            "tile_elems": self.last_tile_elems, "bias_off": bias_off}
+                            "tile_elems": self.FLAG_GRANULE, "bias_off": bias_off}
+
+    def gate_first_conv(self, conv) -> None:
+        """bcast_gemm for a convolutional first layer, usable INSIDE a captured CUDA graph: the staging kernel of the
+        layer's weights and the TMA producer of its GEMM acquire the arrival flags of the arena granules under
+        ``conv.weight`` and compare them with ``self.epoch_word`` -- a device word the session bumps (on the compute
+        stream) every time it launches a collective.  Steps after the first of a round find the flags already there
+        (one cached load), so every replay of the captured step can stay gated."""
+        if self.tile_flags is None:
+            raise RuntimeError("session was created with tile_flags=False")
+        slot = None
+        for name, s in self.arena.slots.items():
+            if s.is_param and self.arena._owner(name) is conv and name.endswith(".weight"):
+                slot = s
+                break
+        if slot is None:
+            raise ValueError("conv weight not found in the arena")
+        conv.flags_cfg = {"flags": self.tile_flags, "epoch_word": self.epoch_word, "elem_off": slot.offset,
+                          "tile_elems": self.FLAG_GRANULE}
 
     def reduced_loss(self, n_epoch: int) -> List[float]:
         return self.loss_out[: min(n_epoch, MAX_LOSS)].tolist()

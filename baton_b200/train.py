@@ -98,6 +98,11 @@ class GraphedLocalSGD:
         # hides: 4.52 vs 4.54 ms per 8 steps, profiles/r2_trace_sgd_overlap.txt) -> opt-in
         self.tail_overlap = os.environ.get("BATON_SGD_OVERLAP", "0") == "1"
         self.tail_ctas = int(os.environ.get("BATON_SGD_TAIL_CTAS", "148"))    # grid cap of the overlapped SGD slice
+        self.k3_join = None           # set by the engine: callable joining the round-end collective (enables the graph split)
+        self._first_gemm_hook = None
+        self.pack = None              # set by the engine: FedAvgSession.pack_spec() -> last SGD step emits the upload copy
+        self.emitted_wire = False
+        self.graph_emits_wire = False
         self._split = None
         self._tail_stream = None
         self._tail_pending = False
@@ -119,10 +124,17 @@ class GraphedLocalSGD:
         loss = self.bnn.mse_loss(out, yb)
         return loss, torch.stack([loss.detach(), torch.zeros_like(loss.detach())])
 
-    def _step(self, X, y, idx):
+    def _gather(self, X, y, idx):
         F = self.F
         xb = F.gather_rows(X, idx)
         yb = F.gather_rows(y, idx) if y.dtype == torch.int64 and y.dim() == 1 else y.index_select(0, idx)
+        return xb, yb
+
+    def _step(self, X, y, idx, batch=None, emit_wire=False):
+        """One SGD step on ``X[idx], y[idx]`` (or on the already gathered ``batch``).  ``emit_wire``: last step of
+        an epoch -- the optimizer kernel also writes the upload copy for the round-end collective (``self.pack``)."""
+        F = self.F
+        xb, yb = batch if batch is not None else self._gather(X, y, idx)
         ws = getattr(self.model, "stats_workspace", None)
         if ws is not None and not getattr(self.model, "zeroes_own_workspace", False):
             ws.zero_()
@@ -136,17 +148,22 @@ class GraphedLocalSGD:
             # of the backward pass and the first layers of the NEXT step's forward.
             split = self._tail_split()
             self._tail_done = False
-            explicit(xb, yb, loss_acc=self.loss_acc, hooks=self if split else None)
+            explicit(xb, yb, loss_acc=self.loss_acc, hooks=self if (split or self._first_gemm_hook is not None) else None)
             end = split if (split and self._tail_done) else a.n_param
-            F.fused_sgd(a.theta[:end], a.grad[:end], self.hyper, a.momentum[:end] if a.momentum is not None else None,
-                        bf[:end] if bf is not None else None, zero_grad=True, nesterov=self.nesterov)
+            pack = self.pack if (emit_wire and end == a.n_param) else None
+            F.fused_sgd(a.theta[:end], a.grad[:end], self.hyper,
+                        a.momentum[:end] if a.momentum is not None else None,
+                        bf[:end] if bf is not None else None, zero_grad=True, nesterov=self.nesterov, pack=pack)
+            self.emitted_wire = pack is not None
             return
         out = self.model(xb)
         loss, stats = self._loss(out, yb)
         loss.backward()
         self.bnn.WGRAD.join()      # weight-gradient GEMMs run on a side stream; they must land before the step
+        pack = self.pack if emit_wire else None
         F.fused_sgd(a.theta[: a.n_param], a.grad, self.hyper, a.momentum,
-                    bf[: a.n_param] if bf is not None else None, zero_grad=True, nesterov=self.nesterov)
+                    bf[: a.n_param] if bf is not None else None, zero_grad=True, nesterov=self.nesterov, pack=pack)
+        self.emitted_wire = pack is not None
         self.loss_acc.add_(stats)
 
     # ---- optimizer / backward overlap (hooks called by ``model.explicit_step``) ----
@@ -184,6 +201,11 @@ class GraphedLocalSGD:
         self._tail_done = True
         self._tail_pending = True
 
+    def after_first_gemm(self):
+        """Called by ``model.explicit_step`` right after the GEMM of the model's first convolution."""
+        if self._first_gemm_hook is not None:
+            self._first_gemm_hook()
+
     def before_tail_forward(self):
         if self._tail_pending:
             torch.cuda.current_stream(self.device).wait_stream(self._tail_stream)
@@ -213,11 +235,51 @@ class GraphedLocalSGD:
         torch.cuda.synchronize(self.device)
         from .ops._ext import total_launches
         graph = torch.cuda.CUDAGraph()
+        graph2 = None
         c0 = total_launches()
-        with torch.cuda.graph(graph):
+
+        def body():
+            # the epoch's batches are gathered by ONE launch pair (a permuted copy of the shard, 25 MB for the
+            # flagship config) instead of two latency-bound gathers at the head of every step
+            Xp, yp = self._gather(X, y, perm)
             for s in range(n_steps):
-                self._step(X, y, perm[s * batch_size:(s + 1) * batch_size])
+                self._step(X, y, None, batch=(Xp[s * batch_size:(s + 1) * batch_size],
+                                              yp[s * batch_size:(s + 1) * batch_size]),
+                           emit_wire=(s == n_steps - 1 and self.pack is not None))
+            self.graph_emits_wire = self.pack is not None
             self.before_tail_forward()       # every forked stream must rejoin before the capture ends
+
+        if self.k3_join is not None and self.explicit and hasattr(self.model, "explicit_step"):
+            # bcast_gemm (K3): the epoch is captured as TWO graphs that share one memory pool.  Graph 1 ends right after
+            # the first convolution's GEMM of the first step -- everything in it either does not touch the parameter
+            # arena (batch gather, im2col) or acquires the collective's arrival flags (weight staging, TMA producer of
+            # the GEMM), so it is replayed WITHOUT waiting for the round-end collective that is still running on its
+            # side stream.  Graph 2 (the rest of the epoch) is replayed after the join.
+            graph2 = torch.cuda.CUDAGraph()
+            pool = torch.cuda.graph_pool_handle()
+            cap = torch.cuda.Stream(device=self.device)
+            cap.wait_stream(torch.cuda.current_stream(self.device))
+            state = {"cut": False}
+
+            def cut():
+                if not state["cut"]:
+                    state["cut"] = True
+                    graph.capture_end()
+                    graph2.capture_begin(pool=pool)
+            self._first_gemm_hook = cut
+            with torch.cuda.stream(cap):
+                graph.capture_begin(pool=pool)
+                try:
+                    body()
+                finally:
+                    self._first_gemm_hook = None
+                (graph2 if state["cut"] else graph).capture_end()
+            torch.cuda.current_stream(self.device).wait_stream(cap)
+            if not state["cut"]:
+                graph2 = None
+        else:
+            with torch.cuda.graph(graph):
+                body()
         self.kernels_per_epoch = total_launches() - c0      # our kernels inside one epoch graph
         self.n_kernels_per_step = self.kernels_per_epoch // max(1, n_steps)
         # undo the side effects of warm-up + capture-time execution (capture does not execute,
@@ -229,7 +291,7 @@ class GraphedLocalSGD:
         self.arena.grad.zero_()
         self.arena.sync_shadow()
         self.loss_acc.zero_()
-        return {"graph": graph, "perm": perm, "X": X, "y": y}
+        return {"graph": graph, "graph2": graph2, "perm": perm, "X": X, "y": y}
 
     # -------------------------------------------------------------- public
     @torch.no_grad()
@@ -261,6 +323,9 @@ class GraphedLocalSGD:
                 ent["perm"].copy_(perm_full[: n_steps * batch_size])
                 self.loss_acc.zero_()
                 ent["graph"].replay()
+                if ent.get("graph2") is not None:
+                    self.k3_join()           # the collective of the previous round must have landed from here on
+                    ent["graph2"].replay()
                 if tail:
                     with torch.enable_grad():
                         self._step(X, y, perm_full[n_steps * batch_size:])
@@ -279,6 +344,9 @@ class GraphedLocalSGD:
                 epoch_losses[e].copy_(self.loss_acc)
         steps = n_steps + (1 if tail else 0)
         self.last_steps = steps
+        self.last_had_tail_step = bool(tail)        # a ragged eager step ran after the graph: its SGD did not emit the wire
+        if self.use_graph:
+            self.emitted_wire = bool(self.graph_emits_wire and not tail)
         if return_device:                     # caller reads (or forwards) the losses itself: no host sync here
             return epoch_losses
         host = epoch_losses.tolist()          # the ONLY host read of the round

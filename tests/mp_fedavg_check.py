@@ -105,8 +105,8 @@ def main():
                       sum((2 * r + 1) * 100.0 * (r + 1) for r in range(world)) / N]
                 got = sess.reduced_loss(2)
                 expect(abs(got[0] - wl[0]) < 1e-4 and abs(got[1] - wl[1]) < 1e-4, tag + " loss history reduce")
-                n_tiles = -(-arena.n // sess.last_tile_elems)
-                expect(int(sess.tile_flags[:n_tiles].min()) == 1, tag + " tile flags published")
+                n_flags = -(-arena.n // sess.FLAG_GRANULE)      # one flag per 1024-element granule, whatever the tile size
+                expect(int(sess.tile_flags[:n_flags].min()) == 1, tag + " tile flags published")
 
                 # partial participation: the last rank reports n_k = 0 (host plan path)
                 torch.manual_seed(200 + rank)

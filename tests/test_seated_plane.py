@@ -173,3 +173,64 @@ async def test_http_control_plane_drives_fused_kernel_on_gpu():
         assert exp.metrics.records[-1]["bytes_http"] < 8192
     finally:
         await fed.close()
+
+
+@run_async
+async def test_seated_plane_distributes_the_model_to_new_and_returning_seats():
+    """A seat that has never been given the global model (first round; re-registration after an eviction) receives
+    the full state_dict inside its round_start -- pulled from a live seat when the manager's copy is stale -- and the
+    aggregation plan carries the manager's round index (the seats derive the collective's barrier epoch from it)."""
+    fed = Federation()
+    exp = await fed.start_manager(dataplane="fused")
+    fabric = FakeFabric()
+    try:
+        ws = []
+        for r in range(2):
+            torch.manual_seed(100 + r)
+            m = LinearModel()                                    # different weights on every seat on purpose
+            ws.append(await fed.add_worker(model=m, n=5, seed=r, dataplane="fused", session=FakeSession(fabric, r, m)))
+        loaded = {0: [], 1: []}
+        for r, w in enumerate(ws):
+            orig = w.model.load_state_dict
+            w.model.load_state_dict = (lambda sd, _o=orig, _r=r, **kw: (loaded[_r].append({k: v.clone() for k, v in sd.items()}),
+                                                                      _o(sd, **kw))[1])
+        init = {k: v.clone() for k, v in exp.model.state_dict().items()}
+        orig_agg = exp.plane.aggregate
+        plans = []
+
+        async def spy(experiment, responses):
+            fabric.snapshot = {w.plane.rank: {k: v.clone() for k, v in w.model.state_dict().items()} for w in ws}
+            plans.append(exp.plane.n_aggregates)
+            return await orig_agg(experiment, responses)
+        exp.plane.aggregate = spy
+        await fed.get("start_round?n_epoch=1")
+        await fed.wait_round_closed()
+        assert len(loaded[0]) == 1 and len(loaded[1]) == 1                       # round 1: everybody got the manager's model
+        for k in init:
+            assert torch.equal(loaded[0][0][k], init[k]) and torch.equal(loaded[1][0][k], init[k])
+        for k, v in ws[0].model.state_dict().items():
+            assert torch.allclose(v, ws[1].model.state_dict()[k])
+        await fed.get("start_round?n_epoch=1")
+        await fed.wait_round_closed()
+        assert len(loaded[0]) == 1 and len(loaded[1]) == 1                       # round 2: metadata only
+        assert plans == [0, 1]
+        # seat 1 is evicted, misses a round, comes back under a new client id
+        exp.client_manager.evict(ws[1].client_id, "test")
+        await fed.get("start_round?n_epoch=1")
+        await fed.wait_round_closed()
+        current = {k: v.clone() for k, v in ws[0].model.state_dict().items()}     # the global model after round 3
+        with torch.no_grad():
+            for v in ws[1].model.state_dict().values():
+                v.add_(1.0)                                                       # its replica is stale / wrong
+        ws[1].client_id = ws[1].key = None
+        await ws[1].register_with_manager()
+        await fed.get("start_round?n_epoch=1")
+        await fed.wait_round_closed()
+        assert len(loaded[0]) == 1 and len(loaded[1]) == 2                       # only the returning seat was re-synced
+        for k in current:
+            assert torch.allclose(loaded[1][1][k], current[k], atol=1e-6), k      # ... with the CURRENT global model
+        for k, v in ws[0].model.state_dict().items():
+            assert torch.allclose(v, ws[1].model.state_dict()[k], atol=1e-6)
+        assert plans == [0, 1, 2, 3]
+    finally:
+        await fed.close()
