@@ -98,6 +98,7 @@ class Experiment:
         self.last_checkpoint: Optional[str] = None
         self._timeout_task: Optional[asyncio.Task] = None
         self._ending = False
+        self._fanout_pending = False
         self._round_bytes = 0
         self.client_manager.add_evict_callback(self._on_client_evicted)
         self.register_handlers()
@@ -197,9 +198,15 @@ class Experiment:
             if ok and client_id in self.client_manager.clients and hasattr(self.plane, "unsynced"):
                 self.client_manager.clients[client_id]["model_synced"] = True
 
-        result = await self.client_manager.notify_clients(
-            "round_start", http_method="POST", data=body, clients=chosen, client_callback=_accepted,
-            per_client_kwargs=per_client)
+        # while the fan-out is in flight the round cannot close on "everybody registered so far has reported": a fast seat
+        # may train and report before a slower seat (e.g. one that is being sent the whole model) has even accepted
+        self._fanout_pending = True
+        try:
+            result = await self.client_manager.notify_clients(
+                "round_start", http_method="POST", data=body, clients=chosen, client_callback=_accepted,
+                per_client_kwargs=per_client)
+        finally:
+            self._fanout_pending = False
         if not self.update_manager.in_progress or self.update_manager.update_name != update_name:
             return dict(result)          # every participant already reported and the round closed meanwhile
         if not self.update_manager:
@@ -240,8 +247,8 @@ class Experiment:
         rec = self.client_manager[client_id]
         rec["last_update"] = update_name
         rec["num_updates"] += 1
-        if not self.update_manager.clients_left:
-            await self.end_round()
+        if not self.update_manager.clients_left and not self._fanout_pending:
+            await self.end_round()       # (during the fan-out, start_round closes the round itself once it is complete)
         return web.json_response("OK")
 
     def _validate_update(self, data) -> Optional[str]:
@@ -372,7 +379,7 @@ class Experiment:
         if self.update_manager.client_drop(client_id):
             log.info("participant %s dropped from %s (%s)", client_id,
                      self.update_manager.update_name, reason)
-            if self.update_manager.in_progress and not self.update_manager.clients_left:
+            if self.update_manager.in_progress and not self.update_manager.clients_left and not self._fanout_pending:
                 try:
                     asyncio.get_running_loop().create_task(self.end_round())
                 except RuntimeError:  # no loop (sync test context)

@@ -170,3 +170,38 @@ async def test_heartbeat_backoff_then_recover():
     finally:
         wmod.asyncio.sleep = real_sleep
         await fed.close()
+
+
+@run_async
+async def test_round_does_not_close_while_the_fan_out_is_still_in_flight():
+    """A fast client trains and reports while a slow peer has not even answered its round_start yet (e.g. it is being
+    sent the whole model): the round must wait for the fan-out to finish instead of closing on "everybody registered
+    so far has reported" -- found on 2 GPUs, where the fast seat finished 4 SGD steps before the 45 MB POST to the
+    returning seat completed (tests/mp_api_check.py)."""
+    import asyncio
+
+    fed = Federation()
+    exp = await fed.start_manager()
+    try:
+        fast = await fed.add_worker(n=5, seed=0)
+        slow = await fed.add_worker(n=5, seed=1)
+        orig = slow.round_start
+
+        async def delayed(request):
+            for _ in range(2000):               # the slow seat answers its round_start only AFTER the fast one reported
+                if exp.update_manager.client_responses:
+                    break
+                await asyncio.sleep(0.01)
+            await asyncio.sleep(0.05)
+            return await orig(request)
+        # re-route the slow worker's handler
+        for r in slow.app.router.routes():
+            if r.resource.canonical.endswith("/round_start"):
+                r._handler = delayed
+        status, body = await fed.get("start_round?n_epoch=1")
+        assert status == 200 and all(body.values()) and len(body) == 2
+        await fed.wait_round_closed()
+        rec = exp.metrics.records[-1]
+        assert rec["n_clients"] == 2, rec           # both updates were aggregated, not just the fast one
+    finally:
+        await fed.close()
