@@ -225,6 +225,18 @@ void fused_sgd(at::Tensor w, at::Tensor g, const std::optional<at::Tensor>& mom,
         "fused_sgd");
 }
 
+void fold_client(at::Tensor acc, at::Tensor theta, const at::Tensor& global_w, const std::optional<at::Tensor>& wb,
+                 const std::optional<at::Tensor>& mom, double nk, int64_t mode, bool reset) {
+  CHECK_CUDA(acc);
+  TORCH_CHECK(acc.scalar_type() == at::kFloat && theta.scalar_type() == at::kFloat && global_w.scalar_type() == at::kFloat);
+  TORCH_CHECK(acc.numel() == theta.numel() && theta.numel() == global_w.numel());
+  const c10::cuda::CUDAGuard guard(acc.device());
+  check(b200_fold_client(acc.data_ptr<float>(), theta.data_ptr<float>(), global_w.data_ptr<float>(), opt_ptr<void>(wb),
+                         opt_ptr<float>(mom), mom.has_value() && mom->defined() ? mom->numel() : 0, theta.numel(),
+                         static_cast<float>(nk), static_cast<int>(mode), reset, cur_stream()),
+        "fold_client");
+}
+
 void weighted_sum(at::Tensor dst, const std::vector<at::Tensor>& srcs, const std::vector<double>& weights) {
   CHECK_CUDA(dst);
   TORCH_CHECK(srcs.size() == weights.size() && !srcs.empty() && srcs.size() <= B200_MAX_RANKS);
@@ -581,6 +593,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dequant_mx", &dequant_mx);
   m.def("fused_sgd", &fused_sgd);
   m.def("weighted_sum", &weighted_sum);
+  m.def("fold_client", &fold_client);
   m.def("cast", &cast);
   m.def("gather_rows", &gather_rows);
   m.def("colsum", &colsum);

@@ -117,6 +117,39 @@ fused_sgd_kernel(float* __restrict__ w, float* __restrict__ g, float* __restrict
   }
 }
 
+// ------------------------------------------------------------------ logical-client fold (time-sliced clients on one GPU)
+// One pass per co-resident logical client:  acc (+)= n_k * (theta - global)   and, if another client follows on this GPU,
+// reset the replica to the global model (theta = global, bf16 shadow, momentum = 0).  mode: 0 = accumulate, 1 = first
+// client (acc = ...), 2 = finish: theta = global + acc / total (no accumulate; `nk` carries 1 / total).
+__global__ void __launch_bounds__(EW_THREADS)
+fold_client_kernel(float* __restrict__ acc, float* __restrict__ theta, const float* __restrict__ global_w,
+                   __nv_bfloat16* __restrict__ wb, float* __restrict__ mom, long long n_mom, long long n, float nk,
+                   int mode, int reset) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const long long nv = n >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nv;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 g = reinterpret_cast<const float4*>(global_w)[i];
+    if (mode == 2) {
+      const float4 a = reinterpret_cast<const float4*>(acc)[i];
+      reinterpret_cast<float4*>(theta)[i] = make_float4(fmaf(a.x, nk, g.x), fmaf(a.y, nk, g.y), fmaf(a.z, nk, g.z),
+                                                        fmaf(a.w, nk, g.w));
+      continue;
+    }
+    const float4 t = reinterpret_cast<const float4*>(theta)[i];
+    float4 a = mode == 1 ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(acc)[i];
+    a.x = fmaf(nk, t.x - g.x, a.x); a.y = fmaf(nk, t.y - g.y, a.y);
+    a.z = fmaf(nk, t.z - g.z, a.z); a.w = fmaf(nk, t.w - g.w, a.w);
+    reinterpret_cast<float4*>(acc)[i] = a;
+    if (reset) {
+      reinterpret_cast<float4*>(theta)[i] = g;
+      if (wb != nullptr) reinterpret_cast<uint2*>(wb)[i] = make_uint2(pack_bf16x2(g.x, g.y), pack_bf16x2(g.z, g.w));
+      if (mom != nullptr && (i << 2) < n_mom) reinterpret_cast<float4*>(mom)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ multi-source weighted sum
 struct WsumArgs {
   const void* src[B200_MAX_RANKS];
@@ -461,6 +494,14 @@ extern "C" int b200_fused_sgd(float* w, float* g, float* mom, void* w_bf16, long
   if (wire_slot != nullptr && ((n & 7) || (pk.n_pack & 7))) return -2;
   launch_pdl(fused_sgd_kernel, max_ctas > 0 ? ew_grid(n >> 2, max_ctas) : ew_grid(n >> 2), EW_THREADS, 0, stream, w, g, mom, reinterpret_cast<__nv_bfloat16*>(w_bf16), n,
                                                                 hyper, zero_grad, nesterov, pk);
+  RET_LAST();
+}
+extern "C" int b200_fold_client(float* acc, float* theta, const float* global_w, void* w_bf16, float* mom, long long n_mom,
+                                long long n, float nk, int mode, int reset, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (n & 3) return -2;
+  launch_pdl(fold_client_kernel, ew_grid(n >> 2), EW_THREADS, 0, stream, acc, theta, global_w,
+             reinterpret_cast<__nv_bfloat16*>(w_bf16), mom, n_mom, n, nk, mode, reset);
   RET_LAST();
 }
 extern "C" int b200_weighted_sum(void* dst, const void* const* srcs, const float* weights, int n_src, long long n,

@@ -163,6 +163,23 @@ __device__ __forceinline__ void accumulate_col_stats(const GemmParams& p, int co
   }
 }
 
+// Same butterflies, but the warp's column sums go to shared memory (`sbuf[0:BN]` sums, `sbuf[BN:2BN]` sums of squares of
+// ONE warp): the four epilogue warps of a CTA are combined there and the CTA issues ONE global atomic per statistic
+// instead of four -- with 256 CTAs (ResNet stem) the atomics of a launch pile up on 2 N addresses and serialise in L2.
+__device__ __forceinline__ void stage_col_stats(float* sbuf, int BNv, int c, const float (&v)[32]) {
+  float s[32], q[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float r = __bfloat162float(__float2bfloat16_rn(v[j]));
+    s[j] = r;
+    q[j] = r * r;
+  }
+  const float cs = warp_colsum32(s), cq = warp_colsum32(q);
+  const int lane = static_cast<int>(lane_id());
+  sbuf[c + lane] = cs;
+  sbuf[BNv + c + lane] = cq;
+}
+
 // alpha / bias / activation of one row chunk.  The (activation, bias) combination is resolved ONCE per chunk
 // with warp-uniform branches into fully unrolled straight-line code; the per-element runtime switch this
 // replaces cost ~900 SASS instructions per 32-column chunk (ncu: profiles/r1_ncu_gemm_qkv_epilogue.txt).
@@ -432,18 +449,25 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     (static_cast<size_t>(row) * p.ldd + static_cast<size_t>(bz_outer) * p.d_outer +
                      static_cast<size_t>(bz_inner) * p.d_inner) * elt;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * elt) % 16 == 0);
+    // fused BatchNorm statistics: the operand ring is drained by now (the accumulator is complete), so its first bytes
+    // hold the per-warp column sums: [4 warps][2 * BN] floats
+    float* sstat = reinterpret_cast<float*>(smem) + q * 2 * BN;
+    const bool want_stats = p.col_stats != nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       tmem_ld_wait();
       const int col0 = n0 + c;
-      if (col0 >= p.N) continue;                  // warp-uniform
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (col0 >= p.N) {                          // warp-uniform
+        if (want_stats) { sstat[c + lane_id()] = 0.f; sstat[BN + c + lane_id()] = 0.f; }
+        continue;
+      }
       transform_chunk<32>(p, col0, v);
-      if (p.col_stats != nullptr) accumulate_col_stats(p, col0, v);
+      if (want_stats) stage_col_stats(sstat, BN, c, v);
       if (!row_ok) continue;
       const bool full = (col0 + 32 <= p.N);
       if (p.atomic_out) {
@@ -481,6 +505,16 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         } else {
           _Pragma("unroll") for (int j = 0; j < 32; ++j) if (col0 + j < p.N) d[j] = __float2bfloat16_rn(v[j]);
         }
+      }
+    }
+    if (want_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+      const float* all = reinterpret_cast<const float*>(smem);
+      for (int i = threadIdx.x - 128; i < 2 * BN; i += 128) {
+        const int col = i < BN ? i : i - BN;
+        if (n0 + col < p.N)
+          atomicAdd(p.col_stats + (i < BN ? 0 : p.N) + n0 + col,
+                    all[i] + all[2 * BN + i] + all[4 * BN + i] + all[6 * BN + i]);
       }
     }
   }

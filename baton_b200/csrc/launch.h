@@ -53,6 +53,9 @@ int b200_gemm_simt(const void* a, const void* b, void* d, const float* bias, int
 int b200_fused_sgd(float* w, float* g, float* mom, void* w_bf16, long long n, const float* hyper, int zero_grad,
                    int nesterov, int max_ctas, const unsigned long long* wire_slot, const float* pack_global,
                    const float* pack_scale, long long n_pack, int wire_fp32, cudaStream_t stream);
+// logical-client fold: acc (+)= nk * (theta - global) [+ reset of the replica]; mode 2: theta = global + acc * nk
+int b200_fold_client(float* acc, float* theta, const float* global_w, void* w_bf16, float* mom, long long n_mom, long long n,
+                     float nk, int mode, int reset, cudaStream_t stream);
 int b200_weighted_sum(void* dst, const void* const* srcs, const float* weights, int n_src, long long n, int dtype,
                       cudaStream_t stream);  // dtype: 0 fp32, 1 bf16
 int b200_cast_f32_bf16(const float* src, void* dst, long long n, cudaStream_t stream);

@@ -162,6 +162,18 @@ def weighted_sum_(dst: torch.Tensor, srcs: Sequence[torch.Tensor], weights: Sequ
     return dst
 
 
+def fold_client(acc: torch.Tensor, theta: torch.Tensor, global_w: torch.Tensor, nk: float, *, first: bool = False,
+                reset: bool = False, w_bf16: Optional[torch.Tensor] = None, momentum: Optional[torch.Tensor] = None) -> None:
+    """Time-sliced logical clients: ``acc (+)= nk * (theta - global)`` in one pass; ``reset`` also returns the replica
+    to the global model (theta, bf16 shadow, momentum) for the next co-resident client."""
+    load().fold_client(acc, theta, global_w, w_bf16, momentum, float(nk), 1 if first else 0, reset)
+
+
+def fold_finish(acc: torch.Tensor, theta: torch.Tensor, global_w: torch.Tensor, total: float) -> None:
+    """``theta = global + acc / total``: the sample-weighted mean replica this GPU uploads for its logical clients."""
+    load().fold_client(acc, theta, global_w, None, None, 1.0 / float(total), 2, False)
+
+
 def cast(src: torch.Tensor, dtype: torch.dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if out is None:
         out = torch.empty(src.shape, dtype=dtype, device=src.device)

@@ -155,7 +155,7 @@ class FederatedEngine:
             self.sync()
             if len(mine) > 1 and self._acc is None:
                 self._acc = torch.zeros_like(a.theta)
-            if len(mine) > 1:
+            if len(mine) > 1 and not a.theta.is_cuda:
                 self._acc.zero_()
             for j, cid in enumerate(mine):
                 X, y = shards(cid)
@@ -166,14 +166,24 @@ class FederatedEngine:
                 losses_dev = ld * nk if losses_dev is None else losses_dev + ld * nk
                 total_n += nk
                 if len(mine) > 1:
-                    self._acc.add_(a.theta - a.global_w, alpha=float(nk))
-                    if j + 1 < len(mine):          # next co-resident client starts from the global model
-                        a.theta.copy_(a.global_w)
-                        a.sync_shadow()
-                        if a.momentum is not None:
-                            a.momentum.zero_()
+                    more = j + 1 < len(mine)           # the next co-resident client starts from the global model
+                    if a.theta.is_cuda:
+                        from ..ops import functional as F     # ONE kernel: fold the delta + reset the replica
+                        F.fold_client(self._acc, a.theta, a.global_w, nk, first=(j == 0), reset=more,
+                                      w_bf16=a.theta_bf16, momentum=a.momentum)
+                    else:
+                        self._acc.add_(a.theta - a.global_w, alpha=float(nk))
+                        if more:
+                            a.theta.copy_(a.global_w)
+                            a.sync_shadow()
+                            if a.momentum is not None:
+                                a.momentum.zero_()
             if len(mine) > 1:
-                torch.add(a.global_w, self._acc, alpha=1.0 / total_n, out=a.theta)
+                if a.theta.is_cuda:
+                    from ..ops import functional as F
+                    F.fold_finish(self._acc, a.theta, a.global_w, total_n)
+                else:
+                    torch.add(a.global_w, self._acc, alpha=1.0 / total_n, out=a.theta)
             if losses_dev is not None and total_n:
                 losses_dev = losses_dev / total_n
         self.last_losses_dev = losses_dev
