@@ -91,6 +91,53 @@ im2col_scalar_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
   }
 }
 
+// small-channel path, shared-memory edition: one CTA builds the col rows of ONE output image row (n, ho).  The KH input
+// rows it needs (KH x W x C elements, 1.3 KB for the 7x7x3 stem at 32x32) are fetched once with 16-byte loads, the
+// 16-byte col vectors are then assembled from shared memory -- the scalar kernel above issued eight 2-byte global loads per
+// vector (10.3 us for the ResNet stem inside the captured step).  Needs (W * C) % 8 == 0 (16-byte aligned image rows).
+__global__ void __launch_bounds__(128)
+im2col_smallc_smem_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, int N, int H, int W, int C,
+                          int KH, int KW, int stride, int pad, int Ho, int Wo, int kp) {
+  griddep_launch_dependents();
+  griddep_wait();
+  extern __shared__ __align__(16) unsigned short srow[];     // [KH][W * C]
+  const int ho = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  const int wc = W * C, wc8 = wc >> 3;
+  const int h0 = ho * stride - pad;
+  for (int i = threadIdx.x; i < KH * wc8; i += blockDim.x) {
+    const int kh = i / wc8, v = i - kh * wc8;
+    const int h = h0 + kh;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (h >= 0 && h < H) val = __ldg(reinterpret_cast<const uint4*>(x + (static_cast<long long>(n) * H + h) * wc) + v);
+    reinterpret_cast<uint4*>(srow)[i] = val;
+  }
+  __syncthreads();
+  const int K = KH * KW * C, kp8 = kp >> 3;
+  const long long row0 = (static_cast<long long>(n) * Ho + ho) * Wo;
+  for (int i = threadIdx.x; i < Wo * kp8; i += blockDim.x) {
+    const int wo = i / kp8, kc0 = (i - wo * kp8) << 3;
+    const int w0 = wo * stride - pad;
+    int tap = kc0 / C, c = kc0 - tap * C;
+    int kh = tap / KW, kw = tap - kh * KW;
+    unsigned short e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int w = w0 + kw;
+      e[j] = (kc0 + j < K && w >= 0 && w < W) ? srow[kh * wc + w * C + c] : static_cast<unsigned short>(0);
+      if (++c == C) {
+        c = 0;
+        if (++kw == KW) { kw = 0; ++kh; }
+      }
+    }
+    uint4 o;
+    o.x = e[0] | (static_cast<uint32_t>(e[1]) << 16);
+    o.y = e[2] | (static_cast<uint32_t>(e[3]) << 16);
+    o.z = e[4] | (static_cast<uint32_t>(e[5]) << 16);
+    o.w = e[6] | (static_cast<uint32_t>(e[7]) << 16);
+    *reinterpret_cast<uint4*>(col + (row0 + wo) * kp + kc0) = o;
+  }
+}
+
 // dX[n,h,w,c] = sum over taps (kh,kw) with ho = (h + pad - kh)/stride, wo = (w + pad - kw)/stride integral
 // and in range of dcol[(n,ho,wo), (kh*KW+kw)*C + c].  One thread per 8 channels, fp32 accumulation.
 __global__ void __launch_bounds__(CV_THREADS)
@@ -333,6 +380,11 @@ extern "C" int b200_im2col_nhwc(const void* x, void* col, int N, int H, int W, i
     launch_pdl(im2col_vec_kernel, cv_grid(rows * (kp / 8)), CV_THREADS, 0, stream, 
         reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(col), N, H, W, C / 8, KH, KW, stride, pad, Ho, Wo,
         kp / 8);
+  } else if (kp % 8 == 0 && (W * C) % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+             static_cast<size_t>(KH) * W * C * 2 <= 48 * 1024) {
+    launch_pdl(im2col_smallc_smem_kernel, dim3(static_cast<unsigned>(N * Ho)), dim3(128),
+               static_cast<size_t>(KH) * W * C * 2, stream, reinterpret_cast<const __nv_bfloat16*>(x),
+               reinterpret_cast<__nv_bfloat16*>(col), N, H, W, C, KH, KW, stride, pad, Ho, Wo, kp);
   } else {
     if (kp % 8) return -2;
     launch_pdl(im2col_scalar_kernel, cv_grid(rows * (kp / 8)), CV_THREADS, 0, stream, 

@@ -139,6 +139,8 @@ class GraphedLocalSGD:
         if ws is not None and not getattr(self.model, "zeroes_own_workspace", False):
             ws.zero_()
         explicit = getattr(self.model, "explicit_step", None) if self.explicit else None
+        if getattr(self.model, "compute_dtype", "bf16") != "bf16":
+            explicit = None            # the hand-scheduled step drives the bf16 conv kernels; MXFP8 convs go through autograd
         a = self.arena
         bf = a.theta_bf16
         if explicit is not None and self.loss_kind in ("ce", "cross_entropy"):
@@ -249,7 +251,8 @@ class GraphedLocalSGD:
             self.graph_emits_wire = self.pack is not None
             self.before_tail_forward()       # every forked stream must rejoin before the capture ends
 
-        if self.k3_join is not None and self.explicit and hasattr(self.model, "explicit_step"):
+        if (self.k3_join is not None and self.explicit and hasattr(self.model, "explicit_step")
+                and getattr(self.model, "compute_dtype", "bf16") == "bf16"):
             # bcast_gemm (K3): the epoch is captured as TWO graphs that share one memory pool.  Graph 1 ends right after
             # the first convolution's GEMM of the first step -- everything in it either does not touch the parameter
             # arena (batch gather, im2col) or acquires the collective's arrival flags (weight staging, TMA producer of
