@@ -559,6 +559,25 @@ void softmax_xent(const at::Tensor& logits, const at::Tensor& target, const std:
                           static_cast<float>(grad_scale), cur_stream()),
         "softmax_xent");
 }
+// False: shape not supported by the one-launch head (more than 32 classes, K % 8, ...)
+bool linear_xent_head(const at::Tensor& x, const at::Tensor& w, const std::optional<at::Tensor>& bias, const at::Tensor& target,
+                      const std::optional<at::Tensor>& dx, at::Tensor dw, const std::optional<at::Tensor>& db,
+                      at::Tensor loss_acc, const std::optional<at::Tensor>& logits_out, double grad_scale) {
+  CHECK_CUDA(x);
+  TORCH_CHECK(x.scalar_type() == at::kBFloat16 && w.scalar_type() == at::kBFloat16 && x.dim() == 2 && w.dim() == 2 &&
+              x.is_contiguous() && w.is_contiguous() && x.size(1) == w.size(1));
+  TORCH_CHECK(target.scalar_type() == at::kLong && dw.scalar_type() == at::kFloat && dw.is_contiguous() &&
+              dw.numel() == w.numel() && loss_acc.scalar_type() == at::kFloat && loss_acc.numel() >= 2);
+  const c10::cuda::CUDAGuard guard(x.device());
+  const int rc = b200_linear_xent_head(x.data_ptr(), w.data_ptr(), opt_ptr<const float>(bias),
+                                       reinterpret_cast<const long long*>(target.data_ptr<int64_t>()), opt_ptr<void>(dx),
+                                       dw.data_ptr<float>(), opt_ptr<float>(db), loss_acc.data_ptr<float>(),
+                                       opt_ptr<float>(logits_out), static_cast<int>(x.size(0)), static_cast<int>(x.size(1)),
+                                       static_cast<int>(w.size(0)), static_cast<float>(grad_scale), cur_stream());
+  if (rc == -2) return false;
+  check(rc, "linear_xent_head");
+  return true;
+}
 void mse(const at::Tensor& pred, const at::Tensor& target, const std::optional<at::Tensor>& dpred, at::Tensor loss_acc,
          double grad_scale) {
   CHECK_CUDA(pred);
@@ -621,4 +640,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("softmax_bwd", &softmax_bwd);
   m.def("softmax_xent", &softmax_xent);
   m.def("mse", &mse);
+  m.def("linear_xent_head", &linear_xent_head);
 }

@@ -273,7 +273,7 @@ __device__ __forceinline__ void store_row_chunk(const GemmParams& p, int row, in
 // [64 cout] x [BN cin] slab of that tap inside the channels_last weight matrix, loaded MN-major (no weight transpose,
 // no col2im).  See csrc/im2col_tma.cu for the tensor maps.
 template <int BN, int STAGES, int CONV = 0>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)      // <= 128 registers: two shallow-ring CTAs may share an SM
 gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
   using L = SmemLayout<BN>;
@@ -335,6 +335,7 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                              p.flag_tile_elems, need);
         fence_proxy_async_all();  // order the acquires before the async-proxy (TMA) reads of global memory
       }
+      TRACE_POINT();  // fixed: producer starts issuing TMA
       for (int i = 0; i < num_kt; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
@@ -419,6 +420,7 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
       if (elect_one()) {
+        if (i == 0) TRACE_POINT();  // fixed: first k-tile landed in smem
         const uint32_t sa = smem_u32(smem + s * L::STAGE_BYTES);
         const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
@@ -437,11 +439,20 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       __syncwarp();
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue =====================
+  }
+  {
+    // ===================== epilogue: ALL EIGHT WARPS =====================
+    // A warp can only read the TMEM lane quarter (warp % 4), but two warps may share a quarter: once the producer / MMA /
+    // allocator warps have finished their roles they join, so the BN accumulator columns are drained by eight warps
+    // instead of four (warps 4-7 take the first half of the 32-column chunks, warps 0-3 the second).  The epilogue was
+    // 1.2 us (2.0 us with fused BatchNorm statistics) of a 5-7 us latency-bound conv GEMM (intra-kernel timeline,
+    // profiles/r2_gemm_anatomy_*.txt).
     const int q = warp & 3;
+    constexpr int NCHUNK = BN / 32;
+    const int c_begin = (warp >= 4 ? 0 : (NCHUNK + 1) / 2) * 32, c_end = (warp >= 4 ? (NCHUNK + 1) / 2 : NCHUNK) * 32;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    if (threadIdx.x == 128) TRACE_POINT();  // fixed: accumulator complete (epilogue starts)
     const int row = m0 + q * 32 + static_cast<int>(lane_id());
     const bool row_ok = row < p.M;
     const size_t elt = p.out_fp32 ? 4 : 2;
@@ -454,7 +465,7 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     float* sstat = reinterpret_cast<float*>(smem) + q * 2 * BN;
     const bool want_stats = p.col_stats != nullptr;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       tmem_ld_wait();
@@ -507,10 +518,11 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
       }
     }
+    if (threadIdx.x == 128) TRACE_POINT();  // fixed: epilogue stores issued
     if (want_stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+      __syncthreads();                                     // all eight warps staged their column sums
       const float* all = reinterpret_cast<const float*>(smem);
-      for (int i = threadIdx.x - 128; i < 2 * BN; i += 128) {
+      for (int i = threadIdx.x; i < 2 * BN; i += GEMM_THREADS) {
         const int col = i < BN ? i : i - BN;
         if (n0 + col < p.N)
           atomicAdd(p.col_stats + (i < BN ? 0 : p.N) + n0 + col,
@@ -521,6 +533,7 @@ gemm_bf16_fixed_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TRACE_POINT();  // fixed: all warps done (before TMEM dealloc / exit)
   if (warp == 2) tmem_dealloc(tmem_base, BN);
 }
 
@@ -1071,9 +1084,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       __syncwarp();
       if (++s == STAGES) { s = 0; ph ^= 1; }
     }
-  } else if (warp >= 4) {
-    // ===================== epilogue (phase 1) =====================
+  }
+  {
+    // ===================== epilogue (phase 1): all eight warps (see the fixed kernel) =====================
     const int q = warp & 3;
+    constexpr int NCHUNK = BN / 32;
+    const int c_begin = (warp >= 4 ? 0 : (NCHUNK + 1) / 2) * 32, c_end = (warp >= 4 ? (NCHUNK + 1) / 2 : NCHUNK) * 32;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int lrow = q * 32 + static_cast<int>(lane_id());
@@ -1082,7 +1098,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) && ((p.ldd * elt) % 16 == 0);
     float* part = reinterpret_cast<float*>(smem);  // cluster mode: reuse the (drained) operand ring
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       uint32_t r[32];
       tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
       tmem_ld_wait();

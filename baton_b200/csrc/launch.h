@@ -154,6 +154,10 @@ int b200_softmax_bwd(const void* y, const void* dy, void* dx, long long rows, in
 // ---- loss.cu
 int b200_softmax_xent(const void* logits, int logits_fp32, const long long* target, void* dlogits, int dl_fp32,
                       float* loss_acc, long long rows, int C, long long ld, float grad_scale, cudaStream_t stream);
+// linear classifier head + softmax cross-entropy, forward AND backward, one launch (classes <= 32)
+int b200_linear_xent_head(const void* x, const void* w, const float* bias, const long long* target, void* dx, float* dw,
+                          float* db, float* loss_acc, float* logits_out, int rows, int K, int NC, float grad_scale,
+                          cudaStream_t stream);
 int b200_mse(const void* pred, int pred_fp32, const float* target, void* dpred, int dp_fp32, float* loss_acc,
              long long n, float grad_scale, cudaStream_t stream);
 }

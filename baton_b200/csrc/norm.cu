@@ -73,6 +73,16 @@ bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, uint
   griddep_launch_dependents();
   griddep_wait();
   extern __shared__ float sm[];  // scale[C], shift[C]
+  // the activation (and residual) do not depend on the statistics: issue this thread's first loads BEFORE the
+  // scale / shift phase, so the two global round trips of this latency-bound kernel overlap instead of adding up
+  const int C8 = C >> 3;
+  const long long total = rows * C8;
+  const long long i_first = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  uint4 xv0 = make_uint4(0u, 0u, 0u, 0u), rv0 = make_uint4(0u, 0u, 0u, 0u);
+  if (i_first < total) {
+    xv0 = x[i_first];
+    if (res != nullptr) rv0 = res[i_first];
+  }
   if (training && nbt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;  // num_batches_tracked
   float* scale = sm;
   float* shift = sm + C;
@@ -101,18 +111,15 @@ bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, uint
     }
   }
   __syncthreads();
-  const int C8 = C >> 3;
-  const long long total = rows * C8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+  for (long long i = i_first; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c0 = static_cast<int>(i % C8) * 8;
-    const uint4 xv = x[i];
-    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-    uint32_t rs[4] = {0u, 0u, 0u, 0u};
-    if (res != nullptr) {
-      const uint4 rv = res[i];
-      rs[0] = rv.x; rs[1] = rv.y; rs[2] = rv.z; rs[3] = rv.w;
+    uint4 xv = xv0, rv = rv0;
+    if (i != i_first) {
+      xv = x[i];
+      if (res != nullptr) rv = res[i];
     }
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const uint32_t rs[4] = {rv.x, rv.y, rv.z, rv.w};
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -43,6 +43,21 @@ __device__ __forceinline__ void trace_stamp(long long tag) {
     }
   }
 }
+// intra-kernel stamp from ANY single thread of CTA (0,0,0) (the caller guarantees one thread executes it)
+__device__ __forceinline__ void trace_point(long long tag) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long* p = b200_trace_ptr;
+    if (p != nullptr) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      const unsigned long long i = atomicAdd(p, 1ull);
+      if (i < p[1]) {
+        p[2 + 2 * i] = t;
+        p[3 + 2 * i] = static_cast<unsigned long long>(tag);
+      }
+    }
+  }
+}
 static int b200_trace_set_local(unsigned long long* p) {
   return static_cast<int>(cudaMemcpyToSymbol(b200_trace_ptr, &p, sizeof(p)));
 }
@@ -50,6 +65,7 @@ static int b200_trace_set_local(unsigned long long* p) {
   extern "C" int b200_trace_set_##tu(unsigned long long* p) { return b200::b200_trace_set_local(p); }
 #else
 __device__ __forceinline__ void trace_stamp(long long) {}
+__device__ __forceinline__ void trace_point(long long) {}
 #define B200_TRACE_REGISTER(tu) \
   extern "C" int b200_trace_set_##tu(unsigned long long*) { return -1; }
 #endif
@@ -62,6 +78,9 @@ __device__ __forceinline__ void griddep_launch_dependents_tagged(long long tag) 
   trace_stamp(-tag);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// TRACE_POINT(): intra-kernel timeline stamp (trace build only), tag = 5e9 + TU * 100000 + line; the label is the comment
+// on the same source line
+#define TRACE_POINT() trace_point(5000000000ll + static_cast<long long>(B200_TU_TAG) * 100000 + __LINE__)
 #define griddep_wait() griddep_wait_tagged(static_cast<long long>(B200_TU_TAG) * 100000 + __LINE__)
 #define griddep_launch_dependents() griddep_launch_dependents_tagged(static_cast<long long>(B200_TU_TAG) * 100000 + __LINE__)
 

@@ -221,13 +221,22 @@ class ResNet(FederatedModule):
         else:
             ca = bnn.Ctx()
             feat = bnn._AvgPoolFn.forward(ca, h)
-        cl = bnn.Ctx()
         fc = self.fc
-        logits = bnn._LinearFn.forward(cl, feat, fc.weight, fc.bias, bnn._shadow(fc, "weight", fc.weight), fc.act,
-                                       fc.out_fp32, None, None)
-        cl.needs_dx = True
-        stats, dlogits = F.softmax_xent(logits.contiguous(), target, want_grad=True, acc=loss_acc)
-        d = bnn._LinearFn.backward(cl, dlogits)[0]
+        head = None
+        tw, tb = bnn._grad_target(fc.weight), bnn._grad_target(fc.bias)
+        if fc.out_features <= 32 and tw is not None and (fc.bias is None or tb is not None) and fc.act == 0:
+            # classifier head (linear + softmax cross-entropy, forward and backward) in ONE launch
+            head = F.linear_xent_head(feat.contiguous(), bnn._shadow(fc, "weight", fc.weight), fc.bias, target, tw, tb,
+                                      acc=loss_acc)
+        if head is not None:
+            stats, d, _ = head
+        else:
+            cl = bnn.Ctx()
+            logits = bnn._LinearFn.forward(cl, feat, fc.weight, fc.bias, bnn._shadow(fc, "weight", fc.weight), fc.act,
+                                           fc.out_fp32, None, None)
+            cl.needs_dx = True
+            stats, dlogits = F.softmax_xent(logits.contiguous(), target, want_grad=True, acc=loss_acc)
+            d = bnn._LinearFn.backward(cl, dlogits)[0]
         d = d.reshape(h.shape) if ca is None else bnn._AvgPoolFn.backward(ca, d)
         pieces = [d]
         for bi in range(len(tape) - 1, -1, -1):

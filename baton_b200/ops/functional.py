@@ -353,6 +353,21 @@ def softmax_xent(logits: torch.Tensor, target: torch.Tensor, want_grad: bool = T
     return acc, dl
 
 
+def linear_xent_head(x: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tensor], target: torch.Tensor,
+                     dw: torch.Tensor, db: Optional[torch.Tensor], acc: Optional[torch.Tensor] = None,
+                     want_dx: bool = True, want_logits: bool = False):
+    """Classifier head in one launch: ``logits = x w^T + b`` (<= 32 classes), softmax cross-entropy, and the head's whole
+    backward -- ``dx`` (bf16), ``dw += dlogits^T x``, ``db += colsum(dlogits)`` (fp32, accumulated in place), the batch-mean
+    loss / #correct added into ``acc``.  Returns ``(acc, dx, logits)`` or ``None`` when the shape is not supported."""
+    rows, K = x.shape
+    if acc is None:
+        acc = torch.zeros(2, dtype=torch.float32, device=x.device)
+    dx = torch.empty((rows, K), dtype=BF16, device=x.device) if want_dx else None
+    logits = torch.empty((rows, w_bf16.shape[0]), dtype=torch.float32, device=x.device) if want_logits else None
+    ok = load().linear_xent_head(x, w_bf16, bias, target, dx, dw, db, acc, logits, 1.0 / rows)
+    return (acc, dx, logits) if ok else None
+
+
 def mse(pred: torch.Tensor, target: torch.Tensor, want_grad: bool = True):
     acc = torch.zeros(2, dtype=torch.float32, device=pred.device)
     dp = torch.empty_like(pred) if want_grad else None

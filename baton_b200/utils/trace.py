@@ -28,6 +28,21 @@ _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _NAME_CACHE: Dict[int, str] = {}
 
 
+POINT_BASE = 5_000_000_000      # TRACE_POINT() stamps (intra-kernel): tag = POINT_BASE + tu * 100000 + line
+
+
+def point_label(tag: int) -> str:
+    """Label of an intra-kernel stamp = the comment on its source line."""
+    tu, line = divmod(int(tag) - POINT_BASE, 100000)
+    try:
+        with open(os.path.join(_CSRC, _TUS[tu] + ".cu")) as f:
+            src = f.readlines()
+        text = src[line - 1]
+        return text.split("//", 1)[1].strip() if "//" in text else "{}:{}".format(_TUS[tu], line)
+    except (OSError, IndexError):
+        return "point {}:{}".format(tu, line)
+
+
 def kernel_name(tag: int) -> str:
     """``tag = tu * 100000 + line`` -> name of the ``__global__`` function enclosing that source line."""
     tag = abs(int(tag))
@@ -87,7 +102,7 @@ class KernelTrace:
     def timeline(self) -> List[dict]:
         """One row per kernel: start of its critical-path slot (dependencies done), the slot length (until the next
         kernel's dependencies are done) and how long before that its first CTA was already resident (PDL overlap)."""
-        rec = self.records()
+        rec = [r for r in self.records() if abs(r[1]) < POINT_BASE]
         resident = collections.defaultdict(list)
         rows = []
         for t, tag in rec:
@@ -101,6 +116,18 @@ class KernelTrace:
         if rows:
             rows[-1]["slot_ns"] = 0
         return rows
+
+    def points(self) -> List[Tuple[int, str]]:
+        """``[(t_ns, label)]`` of everything in time order: kernel starts (``> name``) and intra-kernel TRACE_POINTs."""
+        out = []
+        for t, tag in self.records():
+            if tag >= POINT_BASE:
+                out.append((t, "    . " + point_label(tag)))
+            elif tag > 0:
+                out.append((t, "> " + kernel_name(tag)))
+            else:
+                out.append((t, "  (resident) " + kernel_name(tag)))
+        return out
 
     def summary(self, skip_first: int = 0) -> List[str]:
         rows = self.timeline()[skip_first:]

@@ -39,8 +39,24 @@ loss.backward()
 bnn.WGRAD.join()
 hyper = torch.tensor([0.05, 0.9, 1e-4, 0.0], device=dev)
 F.fused_sgd(arena.theta[: arena.n_param], arena.grad, hyper, arena.momentum, arena.theta_bf16[: arena.n_param])
-sess = FedAvgSession(arena, n_ctas=8)
+# round 2: the hand-scheduled step (implicit-GEMM conv fwd / dgrad / wgrad, cluster BatchNorm backward with two-piece
+# gradients, byte-argmax max-pool, one-launch classifier head), the optimizer emitting the upload copy (K4), and the
+# collective with arrival flags consumed by the gated first convolution (K3)
+sess = FedAvgSession(arena, n_ctas=8, tile_flags=True)
+sess.gate_first_conv(m.conv1)
+m.explicit_step(x, y)
+sess.arm_prepack(16.0)
+F.fused_sgd(arena.theta[: arena.n_param], arena.grad, hyper, arena.momentum, arena.theta_bf16[: arena.n_param],
+            pack=sess.pack_spec())
+sess.aggregate(my_n=16.0, prepacked=True, on_side_stream=True)
+m.explicit_step(x, y)            # staging kernel + conv1 GEMM acquire the flags while the collective is in flight
+sess.join()
 sess.aggregate(my_n=16.0)
+# fused attention (S = 128, d = 64)
+qkv = torch.randn(2 * 128, 3 * 2 * 64, device=dev).to(BF16).requires_grad_(True)
+os.environ["BATON_FUSED_ATTN"] = "1"
+bnn._FUSED_ATTN = True
+bnn.attention(qkv, 2, 128, 2, 64).sum().backward()
 b = bert_tiny(3)
 ab = ParamArena(b, dev)
 ids = torch.randint(0, 1024, (4, 64), device=dev)

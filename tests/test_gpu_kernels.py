@@ -560,3 +560,32 @@ def test_softmax_xent_and_mse(F, bnn):
     l.backward()
     lr.backward()
     assert torch.allclose(p.grad, p32.grad, atol=1e-6)
+
+
+@pytest.mark.parametrize("rows,K,nc", [(128, 512, 10), (37, 256, 2), (128, 2048, 32), (5, 64, 1)])
+def test_linear_xent_head_one_launch_matches_fp32_reference(F, rows, K, nc):
+    """Classifier head (linear + softmax cross-entropy forward AND backward) in one launch vs plain fp32 PyTorch."""
+    torch.manual_seed(rows + K + nc)
+    dev = _dev()
+    x = torch.randn(rows, K, device=dev).to(BF16)
+    w = (torch.randn(nc, K, device=dev) * 0.05).to(BF16)
+    b = torch.randn(nc, device=dev) * 0.1
+    t = torch.randint(0, nc, (rows,), device=dev)
+    dw = torch.ones(nc, K, device=dev)                 # accumulate semantics
+    db = torch.ones(nc, device=dev)
+    acc = torch.zeros(2, device=dev)
+    out = F.linear_xent_head(x, w, b, t, dw, db, acc=acc, want_logits=True)
+    assert out is not None
+    _, dx, logits = out
+    torch.cuda.synchronize()
+    x32 = x.float().requires_grad_(True)
+    w32 = w.float().requires_grad_(True)
+    b32 = b.clone().requires_grad_(True)
+    ref_logits = x32 @ w32.t() + b32
+    loss = torch.nn.functional.cross_entropy(ref_logits, t)
+    loss.backward()
+    assert _rel(logits, ref_logits) < 1e-4
+    assert abs(float(acc[0]) - float(loss)) < 1e-4 * max(1.0, abs(float(loss)))
+    assert int(acc[1]) == int((ref_logits.argmax(-1) == t).sum())
+    assert _rel(dx, x32.grad) < 1e-2                       # bf16 output
+    assert _rel(dw - 1.0, w32.grad) < 1e-4 and _rel(db - 1.0, b32.grad) < 1e-4
