@@ -67,6 +67,29 @@ class SymmetricBuffer:
     def mc(self, byte_offset: int = 0) -> int:
         return self.mc_ptr + byte_offset if self.mc_ptr else 0
 
+    def measure_link_gbps(self, iters: int = 8, max_bytes: int = 256 << 20) -> Optional[float]:
+        """Measured NVLink bandwidth of THIS box, per direction: every rank pulls its right neighbour's buffer with
+        the copy engine at the same time (peer view -> local scratch), timed with CUDA events on the device.  This
+        is the denominator of the collective's roofline (bench.py), measured in-repo instead of quoted.  ``None``
+        without peers."""
+        if self.handle is None or self.world < 2:
+            return None
+        n = min(self.nbytes, max_bytes) // 16 * 16
+        peer = (self.rank + 1) % self.world
+        src = self.handle.get_buffer(peer, (n,), torch.uint8)
+        dst = torch.empty(n, dtype=torch.uint8, device=self.device)
+        dst.copy_(src)                                   # maps + warms the path
+        torch.cuda.synchronize(self.device)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            dst.copy_(src)
+        e1.record()
+        torch.cuda.synchronize(self.device)
+        self.barrier()
+        return n * iters / (e0.elapsed_time(e1) * 1e-3) / 1e9
+
     def barrier(self) -> None:
         """Host-visible rendezvous barrier (setup/teardown only, never on the hot path)."""
         if self.handle is not None:

@@ -257,8 +257,22 @@ def main(argv=None):
         torch.cuda.synchronize()
         agg_ms.append(a0.elapsed_time(a1))
     agg_us = min(agg_ms) * 1e3
+    link_gbps = None
+    symm = getattr(eng.session, "symm", None)
+    if world > 1 and symm is not None and hasattr(symm, "measure_link_gbps"):
+        try:
+            link_gbps = symm.measure_link_gbps()
+        except Exception as e:              # evidence only: never fail the bench over it
+            sys.stderr.write("link measurement failed: {}\n".format(e))
 
     # ---- (b) end to end through the public API: pinned H2D every round + loss D2H every round ----
+    if eng.logical_clients:      # warm-up: capture the epoch graph over every staging slot a sampled round can use
+        eng.sync()
+        for j, c in enumerate(mine):
+            Xs, ys = eng.stage(*host_shards[c], slot=j)
+            eng.trainer.run(Xs, ys, n_epoch=1, return_device=True, **eng.hp)
+            eng.arena.theta.copy_(eng.arena.global_w)
+            eng.arena.sync_shadow()
     run(pin_shard, 2, read_loss=True)
     barrier()
     n0 = eng.samples_trained
@@ -307,7 +321,8 @@ def main(argv=None):
             "kernels_per_local_step": getattr(eng.trainer, "n_kernels_per_step", None),
             "agg_bcast_us_per_round": agg_us,
             "agg_bcast_wire_bytes": wire_bytes,
-            "agg_bcast_roofline": _roofline(agg_us, wire_bytes, world),
+            "agg_bcast_roofline": _roofline(agg_us, wire_bytes, world, link_gbps),
+            "nvlink_GBps_per_dir_measured_here": link_gbps,
             "final_loss": (res.loss_history[-1] if res and res.loss_history else None),
             "launch_breakdown": dict(launch_counts()),
         }
@@ -317,10 +332,11 @@ def main(argv=None):
     return 0
 
 
-def _roofline(agg_us: float, wire_bytes: int, world: int):
+def _roofline(agg_us: float, wire_bytes: int, world: int, link_gbps=None):
     """Fraction of the NVLink roofline achieved by the fused reduce+broadcast: bytes that must cross
-    one GPU's links in each direction = 2 * (K-1)/K * |wire| (reduce-scatter pull + broadcast push),
-    over the measured 770 GB/s per direction (B200_PROFILING.md).  For K = 1 the bound is local HBM."""
+    one GPU's links in each direction = (K-1)/K * |wire| (reduce-scatter pull and broadcast push use opposite
+    directions), over the per-direction bandwidth measured on THIS box by ``SymmetricBuffer.measure_link_gbps``
+    (fallback: the 770 GB/s of B200_PROFILING.md).  For K = 1 the bound is local HBM."""
     if agg_us <= 0:
         return None
     if world <= 1:
@@ -328,8 +344,10 @@ def _roofline(agg_us: float, wire_bytes: int, world: int):
         floor_us = bytes_hbm / 6482.7e9 * 1e6
         return {"bound": "hbm", "floor_us": floor_us, "fraction_of_measured": floor_us / agg_us}
     inbound = (world - 1) / world * wire_bytes
-    floor_us = inbound / 770e9 * 1e6          # pull and push use opposite directions concurrently
-    return {"bound": "nvlink 770 GB/s/dir (measured)", "floor_us": floor_us, "fraction_of_measured": floor_us / agg_us}
+    bw = (link_gbps or 770.0) * 1e9
+    floor_us = inbound / bw * 1e6             # pull and push use opposite directions concurrently
+    return {"bound": "nvlink {:.0f} GB/s/dir ({})".format(bw / 1e9, "measured in this run" if link_gbps else "B200_PROFILING.md"),
+            "floor_us": floor_us, "fraction_of_measured": floor_us / agg_us}
 
 
 if __name__ == "__main__":
