@@ -176,7 +176,7 @@ linear_xent_head_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
     }
     float loss = 0.f, hit = 0.f, dl = 0.f;
     if (row < rows) {
-      if (logits_out != nullptr && lane < NC) logits_out[static_cast<size_t>(row) * NC + lane] = mine;
+      if (logits_out != nullptr && lane < NC && blockIdx.y == 0) logits_out[static_cast<size_t>(row) * NC + lane] = mine;
       float m = mine;
       int am = lane < NC ? lane : 0x7fffffff;
 #pragma unroll
@@ -197,16 +197,21 @@ linear_xent_head_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
     if (lane == 0) { sred[warp * 2] = loss; sred[warp * 2 + 1] = hit; }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && blockIdx.y == 0) {
     float l = 0.f, h = 0.f;
     for (int r = 0; r < HEAD_ROWS; ++r) { l += sred[r * 2]; h += sred[r * 2 + 1]; }
     atomicAdd(loss_acc, l * grad_scale);
     atomicAdd(loss_acc + 1, h);
   }
+  // the backward outputs are split over blockIdx.y: slice s owns columns [k_lo, k_hi) of dX and dW (the logits above are
+  // recomputed by every slice -- 8 x NC x K FMAs -- which is cheaper than the 16-CTA serial tail it replaces)
+  const int kslice = K / static_cast<int>(gridDim.y);
+  const int k_lo = static_cast<int>(blockIdx.y) * kslice;
   // dX[r, k] = sum_c dl[r, c] W[c, k]
   if (dx != nullptr) {
-    for (int i = threadIdx.x; i < HEAD_ROWS * (K >> 1); i += 256) {
-      const int r = i / (K >> 1), k = (i - r * (K >> 1)) * 2;
+    const int half = kslice >> 1;
+    for (int i = threadIdx.x; i < HEAD_ROWS * half; i += 256) {
+      const int r = i / half, k = k_lo + (i - r * half) * 2;
       if (r0 + r >= rows) continue;
       float a0 = 0.f, a1 = 0.f;
       for (int c = 0; c < NC; ++c) {
@@ -218,14 +223,14 @@ linear_xent_head_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16
     }
   }
   // dW[c, k] += sum_r dl[r, c] X[r, k]  (the bf16-rounded dl the GEMM path would have used is not reproduced: fp32 is closer)
-  for (int i = threadIdx.x; i < NC * K; i += 256) {
-    const int c = i / K, k = i - c * K;
+  for (int i = threadIdx.x; i < NC * kslice; i += 256) {
+    const int c = i / kslice, k = k_lo + (i - c * kslice);
     float a = 0.f;
 #pragma unroll
     for (int r = 0; r < HEAD_ROWS; ++r) a = fmaf(sdl[r * 32 + c], __bfloat162float(sx[r * K + k]), a);
-    atomicAdd(dw + i, a);
+    atomicAdd(dw + c * K + k, a);
   }
-  if (db != nullptr && threadIdx.x < NC) {
+  if (db != nullptr && blockIdx.y == 0 && threadIdx.x < NC) {
     float a = 0.f;
     for (int r = 0; r < HEAD_ROWS; ++r) a += sdl[r * 32 + threadIdx.x];
     atomicAdd(db + threadIdx.x, a);
@@ -278,7 +283,9 @@ extern "C" int b200_linear_xent_head(const void* x, const void* w, const float* 
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = smem;
   }
-  cudaError_t le = launch_pdl(linear_xent_head_kernel, dim3((rows + HEAD_ROWS - 1) / HEAD_ROWS), dim3(256), smem, stream,
+  int ks = 8;                                   // column slices of the backward outputs (grid.y); each a multiple of 8 columns
+  while (ks > 1 && (K % (ks * 8))) ks >>= 1;
+  cudaError_t le = launch_pdl(linear_xent_head_kernel, dim3((rows + HEAD_ROWS - 1) / HEAD_ROWS, ks), dim3(256), smem, stream,
                               reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(w), bias,
                               target, reinterpret_cast<__nv_bfloat16*>(dx), dw, db, loss_acc, logits_out, rows, K, NC,
                               grad_scale);

@@ -186,6 +186,13 @@ def main():
 
     # fault injection: a peer that never joins the collective must turn into an error status on the
     # waiting ranks (bounded spin), not a hang -- and the session must be usable again afterwards
+    if os.environ.get("BATON_CHECK_SKIP_DEAD_PEER") == "1":      # under compute-sanitizer the bounded spin takes minutes
+        log(rank, "skip dead-peer injection (BATON_CHECK_SKIP_DEAD_PEER=1)")
+        dist.barrier()
+        if rank == 0:
+            print("RESULT", "PASS" if not failures else "FAIL", len(failures), flush=True)
+        dist.destroy_process_group()
+        sys.exit(1 if failures else 0)
     torch.manual_seed(0)
     net = Net()
     arena = ParamArena(net, dev)
