@@ -484,6 +484,43 @@ void bn_bwd_apply(const at::Tensor& x, const at::Tensor& y, const at::Tensor& dy
                           cur_stream()),
         "bn_bwd_apply");
 }
+// ResNet stem: BatchNorm + ReLU + max-pool in one pass (the normalised activation is never materialised) and its backward;
+// false = shape not supported, use the separate kernels
+bool bn_relu_maxpool(const at::Tensor& z, at::Tensor p, at::Tensor arg, at::Tensor sums,
+                     const std::optional<at::Tensor>& gamma, const std::optional<at::Tensor>& beta,
+                     const std::optional<at::Tensor>& rmean, const std::optional<at::Tensor>& rvar, at::Tensor save_mean,
+                     at::Tensor save_rstd, const std::optional<at::Tensor>& nbt, int64_t N, int64_t H, int64_t W, int64_t C,
+                     int64_t k, int64_t stride, int64_t pad, int64_t Ho, int64_t Wo, double eps, double momentum) {
+  CHECK_CUDA(z);
+  const c10::cuda::CUDAGuard guard(z.device());
+  const int rc = b200_bn_relu_maxpool(z.data_ptr(), p.data_ptr(), arg.data_ptr(), sums.data_ptr<float>(),
+                                      opt_ptr<const float>(gamma), opt_ptr<const float>(beta), opt_ptr<float>(rmean),
+                                      opt_ptr<float>(rvar), save_mean.data_ptr<float>(), save_rstd.data_ptr<float>(),
+                                      opt_ptr<long long>(nbt), static_cast<int>(N), static_cast<int>(H), static_cast<int>(W),
+                                      static_cast<int>(C), static_cast<int>(k), static_cast<int>(stride),
+                                      static_cast<int>(pad), static_cast<int>(Ho), static_cast<int>(Wo),
+                                      static_cast<float>(eps), static_cast<float>(momentum), cur_stream());
+  if (rc == -2) return false;
+  check(rc, "bn_relu_maxpool");
+  return true;
+}
+bool bn_maxpool_bwd(const at::Tensor& z, const at::Tensor& p, const at::Tensor& arg, const at::Tensor& dy_a,
+                    const std::optional<at::Tensor>& dy_b, at::Tensor dz, const std::optional<at::Tensor>& gamma,
+                    const at::Tensor& mean, const at::Tensor& rstd, at::Tensor sums, const std::optional<at::Tensor>& dgamma,
+                    const std::optional<at::Tensor>& dbeta, int64_t N, int64_t H, int64_t W, int64_t C, int64_t k,
+                    int64_t stride, int64_t pad, int64_t Ho, int64_t Wo) {
+  CHECK_CUDA(z);
+  const c10::cuda::CUDAGuard guard(z.device());
+  const int rc = b200_bn_maxpool_bwd(z.data_ptr(), p.data_ptr(), arg.data_ptr(), dy_a.data_ptr(), opt_ptr<const void>(dy_b),
+                                     dz.data_ptr(), opt_ptr<const float>(gamma), mean.data_ptr<float>(),
+                                     rstd.data_ptr<float>(), sums.data_ptr<float>(), opt_ptr<float>(dgamma),
+                                     opt_ptr<float>(dbeta), static_cast<int>(N), static_cast<int>(H), static_cast<int>(W),
+                                     static_cast<int>(C), static_cast<int>(k), static_cast<int>(stride),
+                                     static_cast<int>(pad), static_cast<int>(Ho), static_cast<int>(Wo), cur_stream());
+  if (rc == -2) return false;
+  check(rc, "bn_maxpool_bwd");
+  return true;
+}
 // experimental single-kernel BatchNorm backward; false = shape not supported, use reduce + apply
 bool bn_bwd_fused(const at::Tensor& x, const at::Tensor& y, const at::Tensor& dy, at::Tensor dx,
                   const std::optional<at::Tensor>& dres, const std::optional<at::Tensor>& gamma, const at::Tensor& mean,
@@ -634,6 +671,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_apply", &bn_apply);
   m.def("bn_bwd_reduce", &bn_bwd_reduce);
   m.def("bn_bwd_apply", &bn_bwd_apply);
+  m.def("bn_relu_maxpool", &bn_relu_maxpool);
+  m.def("bn_maxpool_bwd", &bn_maxpool_bwd);
   m.def("layernorm_fwd", &layernorm_fwd);
   m.def("layernorm_bwd", &layernorm_bwd);
   m.def("softmax_fwd", &softmax_fwd);

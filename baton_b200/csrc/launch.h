@@ -137,6 +137,14 @@ int b200_bn_bwd_reduce(const void* x, const void* y, const void* dy, const float
 int b200_bn_bwd_apply(const void* x, const void* y, const void* dy, void* dx, void* dres, const float* gamma,
                       const float* save_mean, const float* save_rstd, float* sums, float* dgamma, float* dbeta,
                       long long rows, int C, int relu, cudaStream_t stream);
+int b200_bn_relu_maxpool(const void* z, void* p, void* argmax, const float* sums, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float* save_mean, float* save_rstd, long long* nbt, int N,
+                         int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, float eps, float momentum,
+                         cudaStream_t stream);
+int b200_bn_maxpool_bwd(const void* z, const void* p, const void* argmax, const void* dy_a, const void* dy_b, void* dz,
+                        const float* gamma, const float* save_mean, const float* save_rstd, float* sums, float* dgamma,
+                        float* dbeta, int N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                        cudaStream_t stream);
 int b200_bn_bwd_cluster(const void* x, const void* y, const void* dy_a, const void* dy_b, void* dx, void* dres,
                         const float* gamma, const float* save_mean, const float* save_rstd, float* dgamma, float* dbeta,
                         long long rows, int C, int relu, int max_cluster, cudaStream_t stream);

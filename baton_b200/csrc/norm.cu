@@ -1098,6 +1098,222 @@ static inline dim3 colred_grid(long long rows, int C) {
   if (gy < 1) gy = 1;
   return dim3((C / 2 + 31) / 32, static_cast<unsigned>(gy));
 }
+// ------------------------------------------------------------------ ResNet stem: BatchNorm + ReLU + max-pool fused
+// The stem's normalised activation y = relu(bn(z)) (32768 x 64 for 32x32 inputs) is only ever consumed by the 3x3/2
+// max-pool, and the backward pass needs it only as the ReLU mask at the pooled maxima -- which the pooled output itself
+// carries (p > 0  <=>  y > 0 at the argmax).  So y is never materialised:
+//   forward : p, argmax = maxpool(relu(scale * z + shift))                       (one kernel instead of two, -8 MB)
+//   backward: the per-channel sums of BatchNorm's backward run over the POOLED gradient (4x fewer rows; z is gathered
+//             at the argmax), and the apply pass gathers the pooled gradient while it writes dz (no dense dy).
+// Candidates are rounded to bf16 before they are compared, so p / argmax are bit-identical to bn_apply + maxpool.
+__global__ void __launch_bounds__(256)
+bn_relu_maxpool_kernel(const uint4* __restrict__ z, uint4* __restrict__ p, uint2* __restrict__ arg,
+                       const float* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ save_mean,
+                       float* __restrict__ save_rstd, long long* __restrict__ nbt, int N, int H, int W, int C, int k,
+                       int stride, int pad, int Ho, int Wo, float eps, float momentum) {
+  griddep_launch_dependents();
+  griddep_wait();
+  extern __shared__ float sm[];  // scale[C], shift[C]
+  float* scale = sm;
+  float* shift = sm + C;
+  const long long rows = static_cast<long long>(N) * H * W;
+  if (nbt != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
+  const float inv_rows = 1.f / static_cast<float>(rows);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = sums[c] * inv_rows;
+    const float var = fmaxf(sums[C + c] * inv_rows - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float g = gamma != nullptr ? gamma[c] : 1.f;
+    scale[c] = g * rstd;
+    shift[c] = (beta != nullptr ? beta[c] : 0.f) - mean * g * rstd;
+    if (blockIdx.x == 0) {
+      save_mean[c] = mean;
+      save_rstd[c] = rstd;
+      if (running_mean != nullptr) {
+        const float unbiased = rows > 1 ? var * static_cast<float>(rows) / static_cast<float>(rows - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long long total = static_cast<long long>(N) * Ho * Wo * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    long long t = i / C8;
+    const int wo = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    float sc[8], sh[8], m[8];
+    uint32_t a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[c8 * 8 + j]; sh[j] = shift[c8 * 8 + j]; m[j] = -INFINITY; a[j] = 255u; }
+    for (int kh = 0; kh < k; ++kh) {
+      const int h = ho * stride - pad + kh;
+      if (h < 0 || h >= H) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int w = wo * stride - pad + kw;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8_bn(z[((static_cast<long long>(n) * H + h) * W + w) * C8 + c8], f);
+        const uint32_t tap = static_cast<uint32_t>(kh * k + kw);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float2 y = unpack_bf16x2(pack_bf16x2(fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f),
+                                                     fmaxf(fmaf(f[j + 1], sc[j + 1], sh[j + 1]), 0.f)));
+          if (y.x > m[j]) { m[j] = y.x; a[j] = tap; }
+          if (y.y > m[j + 1]) { m[j + 1] = y.y; a[j + 1] = tap; }
+        }
+      }
+    }
+    p[i] = make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+    arg[i] = make_uint2(a[0] | (a[1] << 8) | (a[2] << 16) | (a[3] << 24), a[4] | (a[5] << 8) | (a[6] << 16) | (a[7] << 24));
+  }
+}
+
+// sums[0:C] += sum_o g[o, c] ;  sums[C:2C] += sum_o g[o, c] * xhat(z at the argmax of o),   g = (dy_a + dy_b) * (p > 0),
+// over the pooled positions o.  Same thread layout / reduction as bn_bwd_reduce_vec_kernel.
+__global__ void __launch_bounds__(256)
+bn_maxpool_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ z, const uint4* __restrict__ p, const uint2* __restrict__ arg,
+                             const uint4* __restrict__ dy_a, const uint4* __restrict__ dy_b,
+                             const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ sums,
+                             int N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo, int rows_per_cta) {
+  griddep_launch_dependents();
+  griddep_wait();
+  extern __shared__ float sm[];
+  const int tpr = C >> 3, rpp = 256 / tpr;
+  const int cg = threadIdx.x % tpr, rg = threadIdx.x / tpr;
+  const long long rows = static_cast<long long>(N) * Ho * Wo;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > rows) r1 = rows;
+  float m[8], rs[8], a[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { m[j] = mean[cg * 8 + j]; rs[j] = rstd[cg * 8 + j]; a[j] = 0.f; q[j] = 0.f; }
+  for (long long r = r0 + rg; r < r1; r += rpp) {
+    const long long o = r * tpr + cg;
+    const uint2 av = arg[o];
+    float g[8], pf[8];
+    unpack8_bn(dy_a[o], g);
+    unpack8_bn(p[o], pf);
+    if (dy_b != nullptr) {
+      float gb[8];
+      unpack8_bn(dy_b[o], gb);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += gb[j];
+    }
+    const int wo = static_cast<int>(r % Wo);
+    const long long t = r / Wo;
+    const int ho = static_cast<int>(t % Ho);
+    const long long n = t / Ho;
+    const int hb = ho * stride - pad, wb = wo * stride - pad;
+    float zf[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int tap = static_cast<int>(((j < 4 ? av.x : av.y) >> (8 * (j & 3))) & 0xffu);
+      const int kh = tap / k, kw = tap - kh * k;
+      zf[j] = 0.f;
+      if (pf[j] > 0.f) zf[j] = __bfloat162float(z[((n * H + (hb + kh)) * W + (wb + kw)) * C + cg * 8 + j]);
+      else g[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a[j] += g[j];
+      q[j] = fmaf(g[j], (zf[j] - m[j]) * rs[j], q[j]);
+    }
+  }
+  colred_finish(a, q, sm, tpr, cg, rg, sums, C);
+}
+
+// dz = gamma * rstd * (g_dense - mean_g - xhat * mean_gx) with g_dense[n, h, w, c] = the pooled gradient of every window
+// whose argmax is (h, w) (ReLU-masked through p > 0), gathered on the fly; block 0 accumulates dgamma / dbeta.
+__global__ void __launch_bounds__(256)
+bn_maxpool_bwd_apply_kernel(const uint4* __restrict__ z, const uint4* __restrict__ p, const uint2* __restrict__ arg,
+                            const uint4* __restrict__ dy_a, const uint4* __restrict__ dy_b, uint4* __restrict__ dz,
+                            const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                            const float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta, int N,
+                            int H, int W, int C, int k, int stride, int pad, int Ho, int Wo) {
+  griddep_launch_dependents();
+  griddep_wait();
+  extern __shared__ float sm[];  // a[C], b[C], m[C], r[C], s[C]
+  float* ka = sm;
+  float* kb = sm + C;
+  float* km = sm + 2 * C;
+  float* kr = sm + 3 * C;
+  float* ks = sm + 4 * C;
+  const long long rows = static_cast<long long>(N) * H * W;
+  const float inv_rows = 1.f / static_cast<float>(rows);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = gamma != nullptr ? gamma[c] : 1.f;
+    const float r = rstd[c];
+    ka[c] = g * r;
+    kb[c] = sums[c] * inv_rows;          // mean of the (dense) gradient
+    km[c] = mean[c];
+    kr[c] = r;
+    ks[c] = sums[C + c] * inv_rows;      // mean of gradient * xhat
+    if (blockIdx.x == 0) {
+      if (dgamma != nullptr) dgamma[c] += sums[C + c];
+      if (dbeta != nullptr) dbeta[c] += sums[c];
+    }
+  }
+  __syncthreads();
+  const int C8 = C >> 3;
+  const long long total = rows * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    long long t = i / C8;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    float xf[8];
+    unpack8_bn(z[i], xf);
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int kh = 0; kh < k; ++kh) {
+      const int hh = h + pad - kh;
+      if (hh < 0 || hh % stride) continue;
+      const int ho = hh / stride;
+      if (ho >= Ho) continue;
+      for (int kw = 0; kw < k; ++kw) {
+        const int ww = w + pad - kw;
+        if (ww < 0 || ww % stride) continue;
+        const int wo = ww / stride;
+        if (wo >= Wo) continue;
+        const long long o = ((static_cast<long long>(n) * Ho + ho) * Wo + wo) * C8 + c8;
+        const uint2 av = arg[o];
+        float f[8], pf[8];
+        unpack8_bn(dy_a[o], f);
+        unpack8_bn(p[o], pf);
+        if (dy_b != nullptr) {
+          float fb[8];
+          unpack8_bn(dy_b[o], fb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += fb[j];
+        }
+        const uint32_t tap = static_cast<uint32_t>(kh * k + kw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t aj = ((j < 4 ? av.x : av.y) >> (8 * (j & 3))) & 0xffu;
+          if (aj == tap && pf[j] > 0.f) g[j] += f[j];
+        }
+      }
+    }
+    uint32_t o4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ca = c8 * 8 + 2 * j, cb = ca + 1;
+      const float xh0 = (xf[2 * j] - km[ca]) * kr[ca], xh1 = (xf[2 * j + 1] - km[cb]) * kr[cb];
+      o4[j] = pack_bf16x2(ka[ca] * (g[2 * j] - kb[ca] - xh0 * ks[ca]), ka[cb] * (g[2 * j + 1] - kb[cb] - xh1 * ks[cb]));
+    }
+    dz[i] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+  }
+}
+
 static inline int stream_grid(long long nvec) {
   long long g = (nvec + 255) / 256;
   if (g < 1) g = 1;
@@ -1332,6 +1548,45 @@ extern "C" int b200_softmax_bwd(const void* y, const void* dy, void* dx, long lo
     RET_LAST();
   }
   launch_pdl(softmax_bwd_kernel, static_cast<unsigned>((rows + 7) / 8), 256, 0, stream, yp, gp, dp, rows, C, scale);
+  RET_LAST();
+}
+
+
+// ---- ResNet stem: BatchNorm + ReLU + max-pool fused (forward) and its two-kernel backward.  Return -2 when the shape is
+// not supported (C % 8, C/8 not a power of two <= 256 for the reduction, window > 255 taps): callers fall back.
+extern "C" int b200_bn_relu_maxpool(const void* z, void* p, void* argmax, const float* sums, const float* gamma,
+                                    const float* beta, float* running_mean, float* running_var, float* save_mean,
+                                    float* save_rstd, long long* nbt, int N, int H, int W, int C, int k, int stride, int pad,
+                                    int Ho, int Wo, float eps, float momentum, cudaStream_t stream) {
+  if (C % 8 || k * k > 255) return -2;
+  const long long total = static_cast<long long>(N) * Ho * Wo * (C / 8);
+  if (total <= 0) return 0;
+  launch_pdl(bn_relu_maxpool_kernel, stream_grid(total), 256, 2 * C * sizeof(float), stream,
+             reinterpret_cast<const uint4*>(z), reinterpret_cast<uint4*>(p), reinterpret_cast<uint2*>(argmax), sums, gamma,
+             beta, running_mean, running_var, save_mean, save_rstd, nbt, N, H, W, C, k, stride, pad, Ho, Wo, eps, momentum);
+  RET_LAST();
+}
+extern "C" int b200_bn_maxpool_bwd(const void* z, const void* p, const void* argmax, const void* dy_a, const void* dy_b,
+                                   void* dz, const float* gamma, const float* save_mean, const float* save_rstd, float* sums,
+                                   float* dgamma, float* dbeta, int N, int H, int W, int C, int k, int stride, int pad, int Ho,
+                                   int Wo, cudaStream_t stream) {
+  if (k * k > 255 || !colred_vec_ok(C, z, p, dy_a) || (dy_b != nullptr && (reinterpret_cast<uintptr_t>(dy_b) & 15)))
+    return -2;
+  const long long prow = static_cast<long long>(N) * Ho * Wo;
+  if (prow <= 0) return 0;
+  int rpc = 2 * (256 / (C >> 3));       // two passes per CTA: 128 CTAs (and 128 atomics per channel) for the 32x32 stem
+  if (rpc < colred_rows_per_cta(prow, C, 2)) rpc = colred_rows_per_cta(prow, C, 2);
+  launch_pdl(bn_maxpool_bwd_reduce_kernel, static_cast<unsigned>((prow + rpc - 1) / rpc), 256, 256 * 16 * sizeof(float),
+             stream, reinterpret_cast<const __nv_bfloat16*>(z), reinterpret_cast<const uint4*>(p),
+             reinterpret_cast<const uint2*>(argmax), reinterpret_cast<const uint4*>(dy_a),
+             reinterpret_cast<const uint4*>(dy_b), save_mean, save_rstd, sums, N, H, W, C, k, stride, pad, Ho, Wo, rpc);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const long long total = static_cast<long long>(N) * H * W * (C / 8);
+  launch_pdl(bn_maxpool_bwd_apply_kernel, stream_grid(total), 256, 5 * C * sizeof(float), stream,
+             reinterpret_cast<const uint4*>(z), reinterpret_cast<const uint4*>(p), reinterpret_cast<const uint2*>(argmax),
+             reinterpret_cast<const uint4*>(dy_a), reinterpret_cast<const uint4*>(dy_b), reinterpret_cast<uint4*>(dz), gamma,
+             save_mean, save_rstd, sums, dgamma, dbeta, N, H, W, C, k, stride, pad, Ho, Wo);
   RET_LAST();
 }
 

@@ -52,6 +52,45 @@ def _conv_bn_bwd(ctxs, dy_a, dy_b=None, needs_dx=True):
     return dx, dres
 
 
+# The stem (conv1 -> bn1 -> relu -> maxpool): BatchNorm + ReLU + max-pool are ONE kernel forward and two backward (the
+# normalised 16x16 activation is never written: the pooled output carries the ReLU mask, BatchNorm's backward sums run
+# over the pooled gradient -- csrc/norm.cu, "ResNet stem").  BATON_STEM_FUSED=0 keeps the separate kernels.
+_STEM_FUSED = __import__("os").environ.get("BATON_STEM_FUSED", "1") != "0"
+
+
+def _stem_fwd(conv, bn, pool, x, after_conv=None):
+    """-> ``(pooled, conv ctx, z, argmax, mean, rstd)`` or ``None`` when the fused kernels do not apply."""
+    stats = conv._fusable_stats(x)
+    if (stats is None or bn.workspace is None or not bn.relu or not bn.training or bn.num_features % 8
+            or bnn._grad_target(bn.weight) is None or bnn._grad_target(bn.bias) is None):
+        return None
+    cc = bnn.Ctx()
+    z = bnn._ConvFn.forward(cc, x, conv.weight, conv._w_bf16(), conv.kernel_size, conv.kernel_size, conv.stride,
+                            conv.padding, None, stats, conv.flags_cfg)
+    if after_conv is not None:
+        after_conv()
+    c = bn.num_features
+    out = bnn.F.bn_relu_maxpool(z, bn.workspace[: 2 * c], bnn._unwrap(bn.weight), bnn._unwrap(bn.bias), bn.running_mean,
+                                bn.running_var, bn.num_batches_tracked, bn.eps, bn.momentum, pool.k, pool.stride, pool.pad)
+    if out is None:
+        raise RuntimeError("bn_relu_maxpool rejected a shape _stem_fwd accepted")
+    p, arg, mean, rstd = out
+    return p, cc, z, arg, mean, rstd
+
+
+def _stem_bwd(saved, bn, pool, dy_a, dy_b=None):
+    p, cc, z, arg, mean, rstd = saved
+    c = bn.num_features
+    gamma = bnn._unwrap(bn.weight)
+    tg, tb = bnn._grad_target(gamma), bnn._grad_target(bnn._unwrap(bn.bias))
+    dz = bnn.F.bn_maxpool_bwd(z, p, arg, dy_a.contiguous(), dy_b.contiguous() if dy_b is not None else None, gamma, mean,
+                              rstd, bn.workspace[2 * c:], tg, tb, pool.k, pool.stride, pool.pad)
+    if dz is None:
+        raise RuntimeError("bn_maxpool_bwd rejected a shape bn_relu_maxpool accepted")
+    cc.needs_dx = False
+    bnn._ConvFn.backward(cc, dz)
+
+
 class BasicBlock(nn.Module):
     expansion = 1
 
@@ -190,7 +229,10 @@ class ResNet(FederatedModule):
             return [d, dx_ds]
         return [d, dres]
 
-    tail_split_prefix = "layer3."       # parameters from here on (layer3, layer4, fc) receive their gradients FIRST
+    # BATON_SGD_OVERLAP=1: parameters from this prefix on receive their gradients first, their optimizer slice runs beside
+    # the rest of the backward pass.  "layer1." = everything but the stem (SGD beside the stem's backward + weight gradient,
+    # which leave most of the GPU idle); "layer3." = the deep layers only (88 % of a ResNet-18; measured neutral)
+    tail_split_prefix = __import__("os").environ.get("BATON_SGD_SPLIT", "layer1.")
 
     def explicit_step(self, x, target, loss_acc=None, hooks=None):
         """Forward + loss + backward of one batch with parameter gradients accumulated into the arena (the same
@@ -202,19 +244,26 @@ class ResNet(FederatedModule):
         step can run beside the rest of the backward pass; ``hooks.before_tail_forward()`` is called before the first
         forward use of those weights."""
         F = bnn.F
+        pre = self.tail_split_prefix or "layer3."
+        tail_layer = int(pre[5]) - 1 if pre.startswith("layer") and pre[5:6].isdigit() else 2
         if self.stats_workspace is not None:
             self.stats_workspace.zero_()
-        h, stem = _conv_bn_fwd(self.conv1, self.bn1, x,
-                               after_conv=getattr(hooks, "after_first_gemm", None) if hooks is not None else None)
-        cp = bnn.Ctx()
-        h = bnn._MaxPoolFn.forward(cp, h, self.maxpool.k, self.maxpool.stride, self.maxpool.pad)
+        after_first = getattr(hooks, "after_first_gemm", None) if hooks is not None else None
+        stem = cp = None
+        fused_stem = _stem_fwd(self.conv1, self.bn1, self.maxpool, x, after_first) if _STEM_FUSED else None
+        if fused_stem is not None:
+            h = fused_stem[0]
+        else:
+            h, stem = _conv_bn_fwd(self.conv1, self.bn1, x, after_conv=after_first)
+            cp = bnn.Ctx()
+            h = bnn._MaxPoolFn.forward(cp, h, self.maxpool.k, self.maxpool.stride, self.maxpool.pad)
         tape = []
         for li, layer in enumerate((self.layer1, self.layer2, self.layer3, self.layer4)):
-            if li == 2 and hooks is not None and getattr(hooks, "_tail_pending", False):
+            if li == tail_layer and hooks is not None and getattr(hooks, "_tail_pending", False):
                 hooks.before_tail_forward()
             for blk in layer:
                 h = self._block_fwd(blk, h, tape)
-        n_head_blocks = len(self.layer1) + len(self.layer2)
+        n_head_blocks = sum(len(l) for l in (self.layer1, self.layer2, self.layer3, self.layer4)[:tail_layer])
         ca = None
         if h.shape[1] == 1 and h.shape[2] == 1:
             feat = h.reshape(h.shape[0], h.shape[3])
@@ -241,10 +290,13 @@ class ResNet(FederatedModule):
         pieces = [d]
         for bi in range(len(tape) - 1, -1, -1):
             pieces = self._block_bwd(tape[bi], pieces)
-            if bi == n_head_blocks and hooks is not None and getattr(hooks, "_split", 0):
+            if bi == n_head_blocks and hooks is not None and getattr(hooks, "_split_active", 0):
                 hooks.tail_grads_ready()
-        d = bnn._MaxPoolFn.backward(cp, pieces[0], pieces[1] if len(pieces) > 1 else None)[0]
-        _conv_bn_bwd(stem, d, needs_dx=False)
+        if fused_stem is not None:
+            _stem_bwd(fused_stem, self.bn1, self.maxpool, pieces[0], pieces[1] if len(pieces) > 1 else None)
+        else:
+            d = bnn._MaxPoolFn.backward(cp, pieces[0], pieces[1] if len(pieces) > 1 else None)[0]
+            _conv_bn_bwd(stem, d, needs_dx=False)
         bnn.WGRAD.join()
         return stats
 

@@ -325,6 +325,39 @@ def maxpool_bwd(dy: torch.Tensor, arg: torch.Tensor, in_shape, k: int, stride: i
     return dx
 
 
+def bn_relu_maxpool(z: torch.Tensor, sums: torch.Tensor, gamma, beta, rmean, rvar, nbt, eps: float, momentum: float,
+                    k: int, stride: int, pad: int):
+    """ResNet stem in one pass: ``maxpool(relu(batchnorm(z)))`` from the conv output ``z`` (NHWC bf16) and the batch
+    statistic sums the conv GEMM's epilogue accumulated, without materialising the normalised activation.
+    -> ``(p, argmax_u8, save_mean, save_rstd)`` or ``None`` when the shape is not supported (callers fall back to
+    ``bn_apply`` + ``maxpool``).  Training mode only."""
+    n, h, w, c = z.shape
+    if c % 8 or k * k > 255:
+        return None
+    ho, wo = conv_out_size(h, k, stride, pad), conv_out_size(w, k, stride, pad)
+    p = torch.empty((n, ho, wo, c), dtype=BF16, device=z.device)
+    arg = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=z.device)
+    mean = torch.empty(c, dtype=torch.float32, device=z.device)
+    rstd = torch.empty(c, dtype=torch.float32, device=z.device)
+    if not load().bn_relu_maxpool(z, p, arg, sums, gamma, beta, rmean, rvar, mean, rstd, nbt, n, h, w, c, k, stride, pad,
+                                  ho, wo, eps, momentum):
+        return None
+    return p, arg, mean, rstd
+
+
+def bn_maxpool_bwd(z: torch.Tensor, p: torch.Tensor, arg: torch.Tensor, dy_a: torch.Tensor, dy_b: Optional[torch.Tensor],
+                   gamma, mean: torch.Tensor, rstd: torch.Tensor, sums_b: torch.Tensor, dgamma, dbeta, k: int, stride: int,
+                   pad: int) -> Optional[torch.Tensor]:
+    """Backward of :func:`bn_relu_maxpool`: ``dz`` from the pooled gradient ``dy_a (+ dy_b)``; ``dgamma`` / ``dbeta``
+    are accumulated in place.  ``sums_b``: zeroed ``[2 * C]`` fp32 scratch.  ``None`` = shape not supported."""
+    n, h, w, c = z.shape
+    dz = torch.empty_like(z)
+    if not load().bn_maxpool_bwd(z, p, arg, dy_a, dy_b, dz, gamma, mean, rstd, sums_b, dgamma, dbeta, n, h, w, c, k, stride,
+                                 pad, p.shape[1], p.shape[2]):
+        return None
+    return dz
+
+
 def avgpool(x: torch.Tensor) -> torch.Tensor:
     n, h, w, c = x.shape
     y = torch.empty((n, c), dtype=BF16, device=x.device)

@@ -104,6 +104,7 @@ class GraphedLocalSGD:
         self.emitted_wire = False
         self.graph_emits_wire = False
         self._split = None
+        self._split_active = 0
         self._tail_stream = None
         self._tail_pending = False
         self._tail_done = False
@@ -148,7 +149,9 @@ class GraphedLocalSGD:
             # branch; the loss kernel accumulates straight into the epoch's running sums.  The optimizer step of the deep
             # layers (their gradients are complete early in the backward pass) runs on a side stream beside the rest
             # of the backward pass and the first layers of the NEXT step's forward.
-            split = self._tail_split()
+            # the epoch's last step emits the upload copy from ONE optimizer launch over the whole arena: no split there
+            split = 0 if (emit_wire and self.pack is not None) else self._tail_split()
+            self._split_active = split
             self._tail_done = False
             explicit(xb, yb, loss_acc=self.loss_acc, hooks=self if (split or self._first_gemm_hook is not None) else None)
             end = split if (split and self._tail_done) else a.n_param

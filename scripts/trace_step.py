@@ -23,6 +23,7 @@ ap.add_argument("--model", default="resnet18")
 ap.add_argument("--steps", type=int, default=8)
 ap.add_argument("--batch-size", type=int, default=128)
 ap.add_argument("--out", default="")
+ap.add_argument("--points", default="", help="kernel name: print the intra-kernel TRACE_POINT stamps of its first 3 launches")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -66,6 +67,19 @@ if len(sgd) >= 3:
     t0 = rows[a]["t_ns"]
     for r in rows[a:b]:
         lines.append("{:9.2f} {:7.2f} {:7.2f}  {}".format((r["t_ns"] - t0) / 1e3, r["slot_ns"] / 1e3, r["early_ns"] / 1e3, r["name"]))
+if args.points:
+    pts = kt.points()
+    shown = 0
+    for i, (t, lab) in enumerate(pts):
+        if lab.startswith("> " + args.points) and shown < 3 and i > len(pts) // 3:
+            shown += 1
+            lines.append("# intra-kernel points of {} (us since its dependencies completed); next kernel start closes the list".format(args.points))
+            prev_end = max((tt for tt, ll in pts[:i] if ll.startswith("> ")), default=t)
+            lines.append("   previous kernel's dependencies done {:8.2f} us earlier".format((t - prev_end) / 1e3))
+            for tt, ll in pts[i + 1: i + 40]:
+                lines.append("{:9.2f}  {}".format((tt - t) / 1e3, ll))
+                if ll.startswith("> "):
+                    break
 text = "\n".join(lines)
 print(text)
 if args.out:

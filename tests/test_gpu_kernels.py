@@ -470,6 +470,73 @@ def test_batchnorm_backward_cluster_kernel_matches_two_kernel_path(bnn, n, h, c,
         assert _rel(dg - 1.0, dgr) < 1e-2 and _rel(db - 1.0, dbr) < 1e-2
 
 
+@pytest.mark.parametrize("n,h,c,two", [(128, 16, 64, True), (8, 16, 64, False), (5, 9, 32, True), (16, 7, 128, True)])
+def test_stem_bn_relu_maxpool_fused_matches_separate_kernels(F, n, h, c, two):
+    """ResNet stem: BatchNorm + ReLU + 3x3/2 max-pool in one kernel (the normalised activation is never written) must be
+    BIT-identical to bn_apply + maxpool, and its backward (BatchNorm sums over the pooled gradient, gather in the apply
+    pass) must match maxpool_bwd + BatchNorm backward and an fp32 autograd oracle."""
+    from baton_b200.ops import load
+    C_ = load()
+    torch.manual_seed(3 + n + h)
+    dev = _dev()
+    k, stride, pad = 3, 2, 1
+    rows = n * h * h
+    z = (torch.randn(n, h, h, c, device=dev) * 1.5 + 0.3).to(BF16)
+    sums = torch.cat([z.float().sum((0, 1, 2)), (z.float() ** 2).sum((0, 1, 2))]).contiguous()
+    gamma = torch.rand(c, device=dev) + 0.5
+    beta = torch.randn(c, device=dev) * 0.3
+    rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    rm2, rv2 = rm.clone(), rv.clone()
+    nbt, nbt2 = torch.zeros((), dtype=torch.long, device=dev), torch.zeros((), dtype=torch.long, device=dev)
+    # separate kernels
+    y = torch.empty_like(z)
+    mean, rstd = torch.empty(c, device=dev), torch.empty(c, device=dev)
+    C_.bn_apply(z, None, y, sums, gamma, beta, rm, rv, mean, rstd, nbt, rows, c, 1e-5, 0.1, True, True)
+    p_ref, arg_ref = F.maxpool(y, k, stride, pad)
+    out = F.bn_relu_maxpool(z, sums, gamma, beta, rm2, rv2, nbt2, 1e-5, 0.1, k, stride, pad)
+    assert out is not None
+    p, arg, mean2, rstd2 = out
+    torch.cuda.synchronize()
+    assert torch.equal(p, p_ref) and torch.equal(arg, arg_ref)
+    assert torch.equal(mean, mean2) and torch.equal(rstd, rstd2)
+    assert torch.equal(rm, rm2) and torch.equal(rv, rv2) and int(nbt2) == 1
+    # backward
+    dy_a = torch.randn_like(p)
+    dy_b = torch.randn_like(p) if two else None
+    dyd = F.maxpool_bwd(dy_a, arg_ref, tuple(z.shape), k, stride, pad, dy_b=dy_b)
+    sb = torch.zeros(2 * c, device=dev)
+    dz_ref, dg_ref, db_ref = torch.empty_like(z), torch.ones(c, device=dev), torch.ones(c, device=dev)
+    C_.bn_bwd_reduce(z, y, dyd, mean, rstd, sb, rows, c, True)
+    C_.bn_bwd_apply(z, y, dyd, dz_ref, None, gamma, mean, rstd, sb, dg_ref, db_ref, rows, c, True)
+    sb2 = torch.zeros(2 * c, device=dev)
+    dg, db = torch.ones(c, device=dev), torch.ones(c, device=dev)
+    dz = F.bn_maxpool_bwd(z, p, arg, dy_a, dy_b, gamma, mean2, rstd2, sb2, dg, db, k, stride, pad)
+    torch.cuda.synchronize()
+    assert dz is not None
+    assert _rel(sb2, sb) < 1e-2            # the separate path rounds the scattered gradient to bf16 first
+    assert _rel(dz, dz_ref) < 1e-2
+    assert _rel(dg - 1.0, dg_ref - 1.0) < 5e-3 and _rel(db - 1.0, db_ref - 1.0) < 5e-3
+    # fp32 autograd oracle of the whole stem tail
+    z32 = z.float().requires_grad_(True)
+    g32, b32 = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    zn = z32.permute(0, 3, 1, 2)
+    yn = torch.relu(torch.nn.functional.batch_norm(zn, None, None, g32, b32, True, 0.1, 1e-5))
+    # the kernels pick the window maximum among bf16-rounded candidates: round with a straight-through estimator so the
+    # oracle routes the gradient to the same positions (exact bf16 ties may still go to another tap: compare dz by
+    # direction and by the fraction of elements that differ, not by the worst element)
+    yq = yn + (yn.to(BF16).float() - yn).detach()
+    pn = torch.nn.functional.max_pool2d(yq, k, stride, pad)
+    dyt = dy_a.float() + (dy_b.float() if dy_b is not None else 0.0)
+    pn.backward(dyt.permute(0, 3, 1, 2))
+    assert _rel(p, pn.permute(0, 2, 3, 1)) < 1e-2
+    ref = z32.grad
+    cos = torch.nn.functional.cosine_similarity(dz.float().flatten(), ref.flatten(), dim=0)
+    assert float(cos) > 0.99, float(cos)
+    bad = ((dz.float() - ref).abs() > 0.05 * ref.abs().max()).float().mean()
+    assert float(bad) < 0.01, float(bad)
+    assert _rel(dg - 1.0, g32.grad) < 3e-2 and _rel(db - 1.0, b32.grad) < 3e-2
+
+
 def test_layernorm_softmax(bnn):
     torch.manual_seed(8)
     dev = _dev()
@@ -562,7 +629,7 @@ def test_softmax_xent_and_mse(F, bnn):
     assert torch.allclose(p.grad, p32.grad, atol=1e-6)
 
 
-@pytest.mark.parametrize("rows,K,nc", [(128, 512, 10), (37, 256, 2), (128, 2048, 32), (5, 64, 1)])
+@pytest.mark.parametrize("rows,K,nc", [(128, 512, 10), (37, 256, 2), (128, 2048, 32), (5, 64, 1), (200, 72, 7)])
 def test_linear_xent_head_one_launch_matches_fp32_reference(F, rows, K, nc):
     """Classifier head (linear + softmax cross-entropy forward AND backward) in one launch vs plain fp32 PyTorch."""
     torch.manual_seed(rows + K + nc)
