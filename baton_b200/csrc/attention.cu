@@ -12,8 +12,8 @@
 //   epilogue O = O~ / rowsum   -> out[b*S + q, h*64 : h*64+64]
 //
 // The S x S scores never touch HBM and P is written exactly once (the unfused path writes S, reads S,
-// writes P, reads P).  EXPERIMENTAL: compiled and wired behind BATON_FUSED_ATTN=1, not yet validated on
-// hardware (round-1 GPU budget ran out) -- the default path stays the three-kernel one.
+// writes P, reads P).  Validated on B200 in round 2 (tests/test_gpu_bert.py, profiles/r2_validate_experimental.txt)
+// and the default since it measured +4.6 % on the BERT-base round (BATON_FUSED_ATTN=0 selects the three-kernel path).
 #define B200_TU_TAG 4
 #include "launch.h"
 #include "pdl.cuh"
@@ -210,7 +210,7 @@ attention_fwd_s128_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 // Every operand tile is a plain [128 rows x 128 B] swizzled block; "K-major" vs "MN-major" is only the descriptor
 // (k-step = 32 B inside a row vs 16 rows = 2048 B, atom stride 16384 B for the two 64-key halves of P / dS).
 // The unfused path reads P twice, writes dP, reads it back, writes dS and reads it twice (all S x S, through HBM);
-// here P is read once and nothing S x S is written.  EXPERIMENTAL, opt-in with the forward (BATON_FUSED_ATTN=1).
+// here P is read once and nothing S x S is written.  Validated and on by default together with the forward (BATON_FUSED_ATTN).
 struct AttnBwdParams {
   __nv_bfloat16* dqkv;     // [B*S, 3*D]
   int H, D;

@@ -88,7 +88,7 @@ void gemm_batched(const at::Tensor& a, const at::Tensor& b, at::Tensor d, int64_
         "gemm_bf16_batched");
 }
 
-// experimental fused attention forward (S = 128, d_head = 64); returns false when the shape is unsupported
+// fused attention forward (S = 128, d_head = 64); returns false when the shape is unsupported
 bool attention_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor probs, int64_t B, int64_t S, int64_t H, int64_t dh,
                    double scale) {
   CHECK_CUDA(qkv); CHECK_CUDA(out); CHECK_CUDA(probs);
@@ -102,7 +102,7 @@ bool attention_fwd(const at::Tensor& qkv, at::Tensor out, at::Tensor probs, int6
   return true;
 }
 
-// experimental: explicit-im2col-layout dump of TMA im2col loads (semantics probe for the implicit-GEMM conv)
+// probe: explicit-im2col-layout dump of TMA im2col loads (semantics probe for the implicit-GEMM conv)
 bool im2col_tma_probe(const at::Tensor& x, at::Tensor col, int64_t kh, int64_t kw, int64_t stride, int64_t pad,
                       int64_t ho, int64_t wo) {
   CHECK_CUDA(x); CHECK_CUDA(col);
@@ -132,7 +132,7 @@ bool attention_bwd(const at::Tensor& qkv, const at::Tensor& dout, const at::Tens
   return true;
 }
 
-// experimental implicit-GEMM convolution; false = shape not supported (caller falls back to im2col + GEMM)
+// implicit-GEMM convolution; false = shape not supported (caller falls back to im2col + GEMM)
 bool conv_igemm_fwd(const at::Tensor& x, const at::Tensor& w, at::Tensor y, int64_t kh, int64_t kw, int64_t stride,
                     int64_t pad, int64_t ho, int64_t wo, int64_t cluster_k, int64_t force_bn,
                     const std::optional<at::Tensor>& col_stats) {
@@ -521,7 +521,7 @@ bool bn_maxpool_bwd(const at::Tensor& z, const at::Tensor& p, const at::Tensor& 
   check(rc, "bn_maxpool_bwd");
   return true;
 }
-// experimental single-kernel BatchNorm backward; false = shape not supported, use reduce + apply
+// single-kernel (grid-barrier) BatchNorm backward, opt-in; false = shape not supported, use reduce + apply
 bool bn_bwd_fused(const at::Tensor& x, const at::Tensor& y, const at::Tensor& dy, at::Tensor dx,
                   const std::optional<at::Tensor>& dres, const std::optional<at::Tensor>& gamma, const at::Tensor& mean,
                   const at::Tensor& rstd, at::Tensor sums, const std::optional<at::Tensor>& dgamma,

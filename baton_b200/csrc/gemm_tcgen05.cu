@@ -1552,7 +1552,7 @@ extern "C" int b200_gemm_bf16_batched(const void* a, const void* b, void* d, int
   return launch_fixed<64, 8>(ta, tb, p, grid, stream);
 }
 
-// ---- implicit-GEMM convolution (EXPERIMENTAL, opt-in from Python with BATON_CONV_IGEMM=1) ---------------------
+// ---- implicit-GEMM convolution (validated on B200 in round 2; the default, BATON_CONV_IGEMM=0 turns it off) ----
 extern "C" int b200_encode_map_im2col_bf16(void* map, const void* x, int N, int H, int W, int C, int KH, int KW,
                                             int stride, int pad, int channels, int pixels);
 

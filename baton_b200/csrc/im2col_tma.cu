@@ -13,7 +13,8 @@
 // This file only contains the encoder, the PTX wrapper and a PROBE kernel that dumps such tiles back to global
 // memory in the layout of the explicit im2col kernel, so the semantics can be pinned down against it
 // (tests/test_gpu_kernels.py::test_tma_im2col_probe_matches_explicit_im2col, opt-in: BATON_TMA_IM2COL=1).
-// EXPERIMENTAL: written after the round-1 GPU budget ran out, never run on hardware, not used by any model path.
+// Semantics probe only (not on any model path): it pinned down the im2col-mode coordinate convention on hardware in
+// round 2 (profiles/r2_validate_experimental.txt) before the implicit-GEMM convolution modes of gemm_tcgen05.cu relied on it.
 #define B200_TU_TAG 5
 #include <cuda.h>
 

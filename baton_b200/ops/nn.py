@@ -319,7 +319,7 @@ class _ConvFn(torch.autograd.Function):
             if kh == 1 and kw == 1 and stride == 1 and pad == 0 and c % 8 == 0:
                 col, ho, wo, kp = x.view(n * h * w, c), h, w, c
             elif _CONV_IGEMM and c % 64 == 0:
-                # experimental: A operand gathered by TMA im2col inside the GEMM, no col buffer (backward: implicit
+                # A operand gathered by TMA im2col inside the GEMM, no col buffer (backward: implicit
                 # wgrad from x itself)
                 ho, wo, kp = F.conv_out_size(h, kh, stride, pad), F.conv_out_size(w, kw, stride, pad), kh * kw * c
                 y = F.conv_igemm_fwd(x, w_bf16, kh, kw, stride, pad, col_stats=stats)
@@ -777,7 +777,7 @@ class _AttnFn(torch.autograd.Function):
         dout = dout.contiguous()
         dqkv = torch.empty_like(qkv)
         if _FUSED_ATTN and S == 128 and dh == 64 and not getattr(ctx, "masked", False):
-            # experimental single-kernel backward (csrc/attention.cu): dP / dS never leave the SM
+            # single-kernel backward (csrc/attention.cu): dP / dS never leave the SM
             if load().attention_bwd(qkv, dout, probs, dqkv, B, S, H, dh, 1.0 / math.sqrt(dh)):
                 return dqkv, None, None, None, None, None
         q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
