@@ -84,8 +84,6 @@ def test_bert_tiny_matches_fp32_reference_and_trains():
     assert hist[-1] < hist[0], hist
 
 
-@pytest.mark.skipif(os.environ.get("BATON_FUSED_ATTN") != "1",
-                    reason="experimental single-kernel attention forward / backward: opt in with BATON_FUSED_ATTN=1")
 def test_fused_attention_forward_and_backward_match_multi_kernel_path():
     from baton_b200.ops import nn as bnn
     torch.manual_seed(0)
@@ -94,6 +92,7 @@ def test_fused_attention_forward_and_backward_match_multi_kernel_path():
     D = H * dh
     qkv = (torch.randn(B * S, 3 * D, device=dev) * 0.5).to(BF16)
     outs = []
+    default = bnn._FUSED_ATTN
     for fused in (False, True):
         bnn._FUSED_ATTN = fused
         x = qkv.clone().requires_grad_(True)
@@ -101,6 +100,6 @@ def test_fused_attention_forward_and_backward_match_multi_kernel_path():
         g = torch.ones_like(out)
         out.backward(g)
         outs.append((out.detach().float(), x.grad.float()))
-    bnn._FUSED_ATTN = True
+    bnn._FUSED_ATTN = default
     assert _rel(outs[1][0], outs[0][0]) < 2e-2
     assert _rel(outs[1][1], outs[0][1]) < 3e-2
