@@ -19,7 +19,6 @@ is host-side by nature.  ``control_plane_ms_per_round`` = round wall time minus 
 from __future__ import annotations
 
 import asyncio
-import json
 import os
 import subprocess
 import sys

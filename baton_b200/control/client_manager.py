@@ -27,7 +27,7 @@ import asyncio
 import logging
 import random
 from datetime import timedelta
-from typing import Awaitable, Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
 from urllib.parse import urljoin
 
 import aiohttp

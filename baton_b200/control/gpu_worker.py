@@ -11,7 +11,7 @@ bootstrap the symmetric-memory rendezvous.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional, Tuple
+from typing import Callable, Tuple
 
 import torch
 

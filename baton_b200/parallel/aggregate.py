@@ -20,7 +20,7 @@ kernel (``ops.weighted_sum_``) instead of K temporaries per key.
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable, List, Mapping, Optional, Sequence
+from typing import List, Mapping, Optional, Sequence
 
 import torch
 
