@@ -18,7 +18,7 @@ Two executions of the same contract:
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Callable, List, Optional
 
 import torch
 from torch import nn
