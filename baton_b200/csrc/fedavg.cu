@@ -319,7 +319,7 @@ __global__ void __maxnreg__(96) fedavg_allreduce_kernel(const __grid_constant__ 
   // ---------------------------------------------------------------- phase 1: reduce + broadcast
   // A remote 16-byte load costs a full NVLink round trip (~2-3 us); with few ranks a thread that handles ONE wire vector
   // per trip has only A loads in flight and the phase runs at a quarter of the link rate (2 GPUs: 54 us for 11 MB each
-  // way, phase stamps in profiles/r2_agg_phases_2gpu.txt).  Each trip therefore handles U vectors, U chosen so that
+  // way, phase stamps as in profiles/r2_agg_bench_8gpu.txt).  Each trip therefore handles U vectors, U chosen so that
   // about eight remote loads per thread are in flight whatever the number of ranks.
   auto reduce_tiles = [&](auto u_tag) {
     constexpr int U = decltype(u_tag)::value;
